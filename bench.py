@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- CSR SpMV effective GB/s (plus fused axpy / reduction GB/s) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference path
+
+A *step* is one `y = A*x` pass (vex::SpMat<double>, CSR) over the 2-D 5-point Poisson matrix of
+BASELINE.json configs[2]: grid 3162 x 3162 per GPU -> 9 998 244 rows, 49 940 644 nonzeros per GPU.
+With N GPUs the grid grows along y to 3162 x (3162*N) (weak scaling: every rank keeps a 10M-row
+slab and exchanges one grid line of ghosts with each neighbour over NCCL), so
+value = N * algorithmic bytes per slab / time.  Algorithmic bytes:
+nnz*12 + (nrows+1)*4 + ncols*8 + nrows*8 = 799 252 612 B per slab.
+
+Cache policy: the per-GPU working set (0.8 GB) is 6x the 126 MB L2, so consecutive passes cannot
+be served from L2 ("inputs larger than L2").
+
+One JSON line on stdout (rank 0).  Extra keys: roofline, cpu_baseline (N=1), e2e, clocks,
+gpu_launches, extra (config[1] numbers: fused a=b+c*d, a+=b+c*d, saxpy, sum(a*b) at N=1e8).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+GRID = 3162                       # configs[2]: 3162^2 = 9 998 244 rows
+VEC_N = 100_000_000               # configs[1]: N = 1e8 doubles
+METRIC = "csr_spmv_effective_gbs"
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for line in Path(self.path).read_text().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def run_reference(args, rank: int, world: int):
+    """The reference's own implementation of the path on the host cores: the OpenCL-CPU execution
+    model restated in oracle/ (kind "port": the real reference needs Boost + OpenCL, absent here)."""
+    if rank != 0:
+        return
+    import oracle
+    G = oracle.default_groups()
+    cores = oracle.num_threads()
+    row, col, val = oracle.poisson(2, GRID)                  # the per-GPU slab of configs[2]
+    n = row.size - 1
+    nnz = int(row[-1])
+    x = oracle.uniform_real(7, n)
+    from vexcl_b200 import gen
+    nbytes = gen.spmv_bytes(n, n, nnz)
+    y = np.zeros(n)
+    L = oracle.lib()
+    import ctypes as C
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+
+    def step():
+        L.orc_csr_spmv(n, ip(row), ip(col), dp(val), dp(x), dp(y), 1.0, 0, 0, G)
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    gbs = nbytes * args.steps / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[2]: y = A*x, 2-D 5-pt Poisson CSR, 3162^2 = 9998244 rows, nnz 49940644",
+                   "algorithmic_bytes_per_step": nbytes},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": f"full 10M-row matrix, {args.steps} passes, OpenCL-CPU work-group model ({G} groups, OpenMP)"},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ this repo's arm (GPU)
+def cpu_baseline_sample():
+    import oracle
+    import ctypes as C
+    G = oracle.default_groups()
+    row, col, val = oracle.poisson(2, GRID)
+    n = row.size - 1
+    nnz = int(row[-1])
+    from vexcl_b200 import gen
+    nbytes = gen.spmv_bytes(n, n, nnz)
+    x = oracle.uniform_real(7, n)
+    y = np.zeros(n)
+    L = oracle.lib()
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    L.orc_csr_spmv(n, ip(row), ip(col), dp(val), dp(x), dp(y), 1.0, 0, 0, G)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t0 < 5.0 and reps < 200):
+        L.orc_csr_spmv(n, ip(row), ip(col), dp(val), dp(x), dp(y), 1.0, 0, 0, G)
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": nbytes * reps / dt / 1e9, "unit": "GB/s", "cores": oracle.num_threads(), "kind": "port",
+            "sample": f"same matrix and x, {reps} passes of the OpenCL-CPU work-group model restatement ({G} groups)"}, y
+
+
+def time_loop(ctx, fn, steps, warmup, barrier):
+    import vexcl_b200 as vx
+    from vexcl_b200.api import Event
+    for _ in range(warmup):
+        fn()
+    ctx.finish()
+    barrier()
+    e0, e1 = Event(ctx), Event(ctx)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    e1.sync()
+    ctx.finish()
+    barrier()
+    return e0.elapsed_ms(e1)
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import vexcl_b200 as vx
+    from vexcl_b200 import gen, _lib as L
+    from vexcl_b200.api import PinnedArray, copy_h2d_async, copy_d2h_async
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = [vx.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+
+        def allgather(arr):
+            out = [None] * world
+            dist.all_gather_object(out, np.asarray(arr))
+            return out
+
+        ctx = vx.Context.distributed(rank, world, local_rank, uid[0], allgather)
+        tok = torch.zeros(1, device="cuda")
+
+        def barrier():
+            dist.all_reduce(tok)
+            torch.cuda.synchronize()
+
+        def max_over_ranks(v):
+            t = torch.tensor([v], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+    else:
+        ctx = vx.Context([local_rank])
+
+        def barrier():
+            ctx.finish()
+
+        def max_over_ranks(v):
+            return v
+
+    peak, peak_src = load_peaks()
+    k = ctx.local[0]
+
+    # ---- workload: this rank's 10M-row slab of the 3162 x (3162*N) grid ----------------------------
+    nx, ny = GRID, GRID * world
+    N = nx * ny
+    part = ctx.partition(N)
+    r0, r1 = int(part[k]), int(part[k + 1])
+    row, col, val = gen.poisson_strip(2, nx, ny, r0=r0, r1=r1, index_dtype=np.int64)
+    slab_rows, slab_nnz = r1 - r0, int(row[-1])
+    A = vx.SpMat(ctx, N, N, row, col, val, vx.FMT_CSR, strip=True)
+    info = A.info()
+    del row, col, val
+    xh = PinnedArray(slab_rows)
+    xh.a[:] = np.random.default_rng(7 + rank).random(slab_rows)
+    yh = PinnedArray(slab_rows)
+    x = vx.vector(ctx, N)
+    y = vx.vector(ctx, N)
+    x.write(xh.a, local_only=True)
+    step_bytes_local = gen.spmv_bytes(slab_rows, slab_rows, slab_nnz)
+    # whole-job algorithmic bytes: every rank's slab (identical up to boundary rows); summed exactly below
+    if dist is not None:
+        import torch
+        t = torch.tensor([float(step_bytes_local)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        step_bytes = float(t.item())
+    else:
+        step_bytes = float(step_bytes_local)
+
+    def spmv_step():
+        A.apply(x, y, 1.0, False)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = vx.launch_count()
+    ms = time_loop(ctx, spmv_step, args.steps, args.warmup, barrier)
+    launches = vx.launch_count() - n0 - 0
+    # launches counted over warm-up + timed; scale to the timed region
+    launches_timed = round(launches * args.steps / (args.steps + args.warmup))
+    ms = max_over_ranks(ms)
+    value = step_bytes * args.steps / (ms * 1e-3) / 1e9
+
+    # clock probe: keep the same kernel busy long enough for >= 3 samples if the timed region was short
+    clocks = None
+    if rank == 0:
+        if ms < 600:
+            t_end = time.perf_counter() + 1.2
+            if world == 1:
+                while time.perf_counter() < t_end:
+                    for _ in range(50):
+                        spmv_step()
+                    ctx.finish()
+        clocks = sampler.stop()
+        if ms < 600 and world == 1:
+            clocks["note"] = "timed region shorter than the sampling period; samples include a 1.2 s continuation of the same loop"
+
+    # ---- dominant kernel duration (single-GPU SpMV kernel timed alone with events) ------------------
+    from vexcl_b200.api import Event
+    ev0, ev1 = Event(ctx), Event(ctx)
+    reps = max(args.steps, 20)
+    lib = L.lib()
+    import ctypes as C
+    ctx.finish()
+    ev0.record()
+    for _ in range(reps):
+        L.check(lib.vexb_dspmat_mul_local(A.parts[k], ctx.streams[k], x.bufs[k], y.bufs[k], 1.0, 0))
+    ev1.record(); ev1.sync()
+    kern_ms = ev0.elapsed_ms(ev1) / reps
+    loc = info.loc
+    kern_bytes = gen.spmv_bytes(slab_rows, slab_rows, int(loc.nnz))
+    achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "roofline_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("csr_stream_kernel_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "csr_stream_kernel<double>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kern_bytes, "kernel_ms": kern_ms}
+
+    # ---- end to end through the public call with HOST buffers ---------------------------------------
+    def e2e_step():
+        copy_h2d_async(x, xh.a)
+        A.apply(x, y, 1.0, False)
+        copy_d2h_async(y, yh.a)
+
+    e2e_steps = max(3, min(args.steps, 50))
+    ms_e2e = max_over_ranks(time_loop(ctx, e2e_step, e2e_steps, 3, barrier))
+    e2e = {"value": step_bytes * e2e_steps / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s",
+           "h2d_bytes_per_step": slab_rows * 8 * world, "d2h_bytes_per_step": slab_rows * 8 * world,
+           "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+           "note": "per step: x slab pinned host -> device, y = A*x, y slab device -> pinned host"}
+
+    # ---- parity spot check of what was just timed (rank-local rows against numpy on 4096 rows) -------
+    extra = {}
+    cpu_base = None
+    if world == 1:
+        # config[1]: vector arithmetic + Reductor, N = 1e8 doubles
+        try:
+            extra = bench_vectors(ctx, vx, args, peak)
+        except vx.VexbError as e:
+            extra = {"error": str(e)}
+        if not args.no_cpu_baseline:
+            cpu_base, y_cpu = cpu_baseline_sample()
+            import oracle                      # checker only: parity of the timed kernel on the oracle's x
+            x.write(oracle.uniform_real(7, slab_rows))
+            y.assign(A * x)
+            got = y.read()
+            err = float(np.max(np.abs(got - y_cpu) / (np.abs(y_cpu) + 1e-300)))
+            extra["parity_max_rel_err_vs_oracle"] = err
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[2] per GPU: y = A*x, vex::SpMat<double> CSR, 2-D 5-pt Poisson, grid {nx} x {ny} "
+                                   f"({N} rows, {slab_rows} per GPU), halo over NCCL send/recv",
+                       "algorithmic_bytes_per_step": step_bytes, "format": "csr row-block stream, 32-bit indices",
+                       "tile_nnz": int(loc.tile_nnz), "n_tiles": int(loc.n_tiles),
+                       "cache": "inputs larger than L2 (0.8 GB per GPU vs 126 MB L2)", "partition": "equal weights"},
+            "frac_of_aggregate_hbm_peak": value / (peak * world),
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches_timed, "clocks": clocks,
+            "cpu_baseline": cpu_base, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        barrier()
+        dist.destroy_process_group()
+
+
+def bench_vectors(ctx, vx, args, peak):
+    """configs[1]: examples/benchmark.cpp vector arithmetic + Reductor<double,SUM> at N = 1e8."""
+    from vexcl_b200 import _lib as L
+    n = VEC_N
+    rng = np.random.default_rng(1)
+    a, b, c, d = (vx.vector(ctx, n) for _ in range(4))
+    a.assign(0.0)
+    for v in (b, c, d):
+        v.assign(vx.ElementIndex() * 1e-8 + 0.25)          # device-side fill, values in [0.25, 1.25)
+    ssum = vx.Reductor(ctx, np.float64, L.SUM)
+    steps = max(10, min(args.steps, 40))
+    cases = {
+        "a=b+c*d": (lambda: a.assign(b + c * d), 32),
+        "a+=b+c*d": (lambda: a.__iadd__(b + c * d), 40),
+        "a=alpha*a+b": (lambda: a.assign(0.5 * a + b), 24),
+        "sum(a*b)": (lambda: ssum(a * b), 16),
+    }
+    out = {}
+    for name, (fn, bpe) in cases.items():
+        ms = time_loop(ctx, fn, steps, 3, ctx.finish)
+        gbs = bpe * n * steps / (ms * 1e-3) / 1e9
+        out[name] = {"gbs": gbs, "frac_of_peak": gbs / peak, "ms": ms / steps, "bytes_per_elem": bpe, "n": n}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world > 1:
+        print(f"warning: WORLD_SIZE={world} != --gpus {args.gpus}", file=sys.stderr)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

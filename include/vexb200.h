@@ -1,0 +1,346 @@
+/*
+ * vexb200.h -- C ABI of libvexb200.so, the Blackwell (sm_100a) compute back end
+ * that sits behind the vex:: C++ front end in include/vexcl/.
+ *
+ * This is the drop-in boundary.  Every entry point
+ * replaces one thing the reference's hot path does through its
+ * `vex::backend` layer (reference paths are relative to /root/reference):
+ *
+ *   lifecycle / props   <- backend::queue_list, backend::device
+ *                          (vexcl/backend/cuda/context.hpp:96-155, :385-413)
+ *   streams / events    <- backend::command_queue, backend::event
+ *                          (vexcl/backend/cuda/context.hpp:205-260, event.hpp:54-123)
+ *   memory              <- backend::device_vector<T> ctor/read/write
+ *                          (vexcl/backend/cuda/device_vector.hpp:66-210)
+ *   vexb_eval           <- detail::assign_expression launch loop body
+ *                          (vexcl/operations.hpp:1818-1897)
+ *   vexb_reduce*        <- Reductor::operator() device stage + host fold
+ *                          (vexcl/reductor.hpp:302-439)
+ *   vexb_partition      <- partitioning_scheme<>::get (vexcl/vector.hpp:131-167)
+ *   vexb_halo_plan_*    <- SpMat::setup_exchange (vexcl/spmat.hpp:291-378)
+ *   vexb_csr_create /
+ *   vexb_spmv           <- SpMatCSR / SpMatHELL ctor + mul_local/mul_remote
+ *                          (vexcl/spmat/csr.inl:45-209, hybrid_ell.inl:53-330)
+ *   vexb_dspmat_*       <- SpMat ctor + SpMat::apply (vexcl/spmat.hpp:71-185)
+ *   vexb_comm_*         <- the host-staged D2H/H2D halo and the host fold of
+ *                          reduction partials (spmat.hpp:149-176,
+ *                          reductor.hpp:412-436), moved to NCCL over NVLink.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0
+ * (VEXB_OK) on success and a vexb_status code otherwise and never throws;
+ * vexb_last_error() returns a thread-local "file:line: message" string for
+ * the last failure on the calling thread.  All `stream` arguments are
+ * cudaStream_t passed as void* (NULL = the legacy default stream).  Device
+ * pointers are owned by the caller unless stated otherwise.  The library is
+ * thread-compatible: concurrent calls that touch different streams/handles
+ * are legal, there is no shared argument stack (contrast
+ * vexcl/backend/cuda/kernel.hpp:44-241).
+ *
+ * There is NO CPU fallback: compute entry points fail with VEXB_ERR_CUDA when
+ * no CUDA device is usable.
+ */
+#ifndef VEXB200_H
+#define VEXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VEXB_ABI_VERSION 1
+
+typedef enum {
+    VEXB_OK = 0,
+    VEXB_ERR_CUDA = 1,        /* a CUDA runtime call failed               */
+    VEXB_ERR_INVALID = 2,     /* bad argument / precondition violated     */
+    VEXB_ERR_NCCL = 3,        /* NCCL missing or an NCCL call failed      */
+    VEXB_ERR_UNSUPPORTED = 4, /* valid request the back end cannot serve  */
+    VEXB_ERR_NOMEM = 5
+} vexb_status;
+
+/* Scalar element types (subset of vexcl/types.hpp:202-260). */
+typedef enum {
+    VEXB_F64 = 0, VEXB_F32 = 1, VEXB_I32 = 2, VEXB_U32 = 3, VEXB_I64 = 4, VEXB_U64 = 5
+} vexb_dtype;
+
+/* Assignment operators, same set and order as vexcl/operations.hpp:70-80. */
+typedef enum {
+    VEXB_SET = 0, VEXB_ADD = 1, VEXB_SUB = 2, VEXB_MUL = 3, VEXB_DIV = 4, VEXB_MOD = 5,
+    VEXB_AND = 6, VEXB_OR = 7, VEXB_XOR = 8, VEXB_LSH = 9, VEXB_RSH = 10
+} vexb_assign;
+
+/* Reduction kinds (vexcl/reductor.hpp:47-128, :132-280). */
+typedef enum {
+    VEXB_SUM = 0, VEXB_SUM_KAHAN = 1, VEXB_MAX = 2, VEXB_MIN = 3,
+    VEXB_MINMAX = 4 /* result[0]=min, result[1]=max, as MIN_MAX (reductor.hpp:262-280) */
+} vexb_reduce_op;
+
+/* ------------------------------------------------------------------------
+ * Expression IR.  The front end lowers a vex:: expression tree to a postfix
+ * program over a table of terminals; this replaces the source text the
+ * reference emits in vexcl/operations.hpp:1209-1353.
+ * ---------------------------------------------------------------------- */
+#define VEXB_MAX_TERMS 16
+#define VEXB_MAX_CODE  64
+#define VEXB_MAX_STACK 12
+
+typedef enum {
+    VEXB_TERM_VEC = 0,    /* v.ptr: device array of `dtype`, element i of this device slice */
+    VEXB_TERM_SCALAR = 1, /* by-value scalar of `dtype` (operations.hpp:168-175)            */
+    VEXB_TERM_INDEX = 2   /* element_index: index_offset + i + v.i64 (element_index.hpp:40-111), type u64 */
+} vexb_term_kind;
+
+typedef struct {
+    uint8_t kind;   /* vexb_term_kind */
+    uint8_t dtype;  /* vexb_dtype     */
+    uint8_t pad[6];
+    union { const void *ptr; double f64; float f32; int32_t i32; uint32_t u32; int64_t i64; uint64_t u64; } v;
+} vexb_term;
+
+/* Opcodes.  `type` of an instruction is the vexb_dtype the node evaluates in
+ * (operands of binary ops must already have that type: the front end inserts
+ * VEXB_OP_CVT following the usual arithmetic conversions).  Comparisons and
+ * logical ops take operands of `type` and produce I32 0/1. */
+typedef enum {
+    VEXB_OP_TERM = 0,  /* push term[arg] converted to nothing: its own dtype            */
+    VEXB_OP_CVT,       /* convert top from dtype `arg` to `type`                         */
+    /* unary */
+    VEXB_OP_NEG, VEXB_OP_LNOT,
+    /* binary arithmetic / bitwise */
+    VEXB_OP_ADD, VEXB_OP_SUB, VEXB_OP_MUL, VEXB_OP_DIV, VEXB_OP_MOD,
+    VEXB_OP_BAND, VEXB_OP_BOR, VEXB_OP_BXOR, VEXB_OP_SHL, VEXB_OP_SHR,
+    /* comparisons / logical (result I32) */
+    VEXB_OP_LT, VEXB_OP_GT, VEXB_OP_LE, VEXB_OP_GE, VEXB_OP_EQ, VEXB_OP_NE,
+    VEXB_OP_LAND, VEXB_OP_LOR,
+    /* ternary: stack [cond(I32) a b] -> cond ? a : b  (if_else, operations.hpp:1277-1301) */
+    VEXB_OP_SELECT,
+    /* builtin functions (vexcl/function.hpp:287-...), floating types only unless noted */
+    VEXB_OP_SIN, VEXB_OP_COS, VEXB_OP_TAN, VEXB_OP_ASIN, VEXB_OP_ACOS, VEXB_OP_ATAN,
+    VEXB_OP_SINH, VEXB_OP_COSH, VEXB_OP_TANH, VEXB_OP_EXP, VEXB_OP_EXP2, VEXB_OP_LOG,
+    VEXB_OP_LOG2, VEXB_OP_LOG10, VEXB_OP_SQRT, VEXB_OP_RSQRT, VEXB_OP_CBRT, VEXB_OP_FABS /* also ints: abs */,
+    VEXB_OP_FLOOR, VEXB_OP_CEIL, VEXB_OP_ROUND, VEXB_OP_TRUNC,
+    VEXB_OP_POW, VEXB_OP_ATAN2, VEXB_OP_FMOD, VEXB_OP_HYPOT,
+    VEXB_OP_FMIN /* also ints: min */, VEXB_OP_FMAX /* also ints: max */,
+    VEXB_OP_FMA,      /* ternary: a*b+c with one rounding (builtin fma)                 */
+    VEXB_OP_COUNT_
+} vexb_opcode;
+
+typedef struct {
+    uint8_t  op;    /* vexb_opcode */
+    uint8_t  type;  /* vexb_dtype  */
+    uint16_t arg;   /* TERM: term slot; CVT: source dtype */
+} vexb_instr;
+
+typedef struct {
+    int32_t    n_terms;
+    int32_t    n_code;
+    vexb_term  term[VEXB_MAX_TERMS];
+    vexb_instr code[VEXB_MAX_CODE];
+} vexb_expr;
+
+/* ------------------------------------------------------------------------
+ * Lifecycle, device properties
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    char     name[256];
+    int32_t  cc_major, cc_minor;
+    int32_t  sm_count;
+    int32_t  max_threads_per_block;
+    int32_t  warp_size;
+    int32_t  pad;
+    size_t   smem_per_block_optin;
+    size_t   total_mem;
+    size_t   l2_bytes;
+} vexb_devprops;
+
+int         vexb_abi_version(void);
+const char *vexb_last_error(void);
+int vexb_init(void);                       /* idempotent; fails loudly when no CUDA device */
+int vexb_shutdown(void);
+int vexb_device_count(int *n);
+int vexb_device_props(int dev, vexb_devprops *p);
+/* Tunables for experiments ("sweep.blocks_per_sm", "spmv.tile_nnz", ...). */
+int vexb_set_param(const char *name, long value);
+int vexb_get_param(const char *name, long *value);
+/* Count of kernels this library has launched from the calling process. */
+int vexb_launch_count(uint64_t *n);
+
+/* ------------------------------------------------------------------------
+ * Streams and events
+ * ---------------------------------------------------------------------- */
+int vexb_stream_create(int dev, void **stream);
+int vexb_stream_destroy(int dev, void *stream);
+int vexb_stream_sync(int dev, void *stream);
+int vexb_device_sync(int dev);
+int vexb_event_create(int dev, void **event);
+int vexb_event_destroy(int dev, void *event);
+int vexb_event_record(int dev, void *event, void *stream);
+int vexb_event_sync(int dev, void *event);
+int vexb_stream_wait_event(int dev, void *stream, void *event);
+int vexb_event_elapsed_ms(void *start, void *stop, float *ms);
+
+/* ------------------------------------------------------------------------
+ * Memory
+ * ---------------------------------------------------------------------- */
+int vexb_malloc(int dev, size_t bytes, void **p);
+int vexb_free(int dev, void *p);
+int vexb_host_alloc(size_t bytes, void **p);   /* pinned host memory */
+int vexb_host_free(void *p);
+int vexb_h2d(int dev, void *dst, const void *src, size_t bytes, void *stream, int blocking);
+int vexb_d2h(int dev, void *dst, const void *src, size_t bytes, void *stream, int blocking);
+int vexb_d2d(int dev, void *dst, const void *src, size_t bytes, void *stream);
+int vexb_memset(int dev, void *dst, int byte, size_t bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Partitioning (host only; no GPU needed)
+ * vexcl/vector.hpp:131-167 with util.hpp:91-93 (alignup 16).
+ * weights == NULL means equal weights (vector.hpp:79-81).
+ * part must hold nparts+1 entries.
+ * ---------------------------------------------------------------------- */
+int vexb_partition(size_t n, int nparts, const double *weights, size_t *part);
+
+/* ------------------------------------------------------------------------
+ * Elementwise: lhs[i] OP= expr(i), i in [0,n) of one device slice.
+ * Replaces the per-device kernel launch of assign_expression
+ * (operations.hpp:1886-1895).  Asynchronous on `stream`.
+ * ---------------------------------------------------------------------- */
+int vexb_eval(int dev, void *stream, void *lhs, int lhs_dtype, int assign_op,
+              const vexb_expr *expr, size_t n, size_t index_offset);
+/* Which kernel vexb_eval would take for this request: writes a short
+ * name ("sweep:muladd", "interp", ...) to buf. */
+int vexb_eval_path(int lhs_dtype, int assign_op, const vexb_expr *expr, char *buf, size_t buflen);
+
+/* ------------------------------------------------------------------------
+ * Reduction of an expression over one device slice to ONE device-resident
+ * value (two for VEXB_MINMAX) of type `dtype`, written to d_result.
+ * d_workspace: at least vexb_reduce_workspace_bytes() bytes of device memory
+ * private to the (device, stream) in use; it must be zero-initialised once
+ * (vexb_memset) before first use and is left reusable after each call.
+ * Replaces reductor.hpp:327-410; the host fold :412-436 is replaced by
+ * vexb_reduce_fetch (single device) or vexb_comm_allreduce (+ fetch).
+ * ---------------------------------------------------------------------- */
+int vexb_reduce_workspace_bytes(int dev, size_t *bytes);
+int vexb_reduce(int dev, void *stream, const vexb_expr *expr, int dtype, size_t n,
+                size_t index_offset, int op, void *d_result, void *d_workspace);
+/* Fill d_result with the identity of `op` (reductor.hpp:55,87,111): used for empty slices. */
+int vexb_reduce_identity(int dev, void *stream, int dtype, int op, void *d_result);
+/* D2H of `count` values + stream sync. */
+int vexb_reduce_fetch(int dev, void *stream, const void *d_result, int dtype, int count, void *host_out);
+
+/* ------------------------------------------------------------------------
+ * Communication (NCCL over NVLink).  NCCL is dlopen()ed on first use.
+ *   single process, n devices : vexb_comm_create_all
+ *   one process per device    : rank 0 calls vexb_comm_unique_id, the 128-byte
+ *                               id is broadcast by the host program, every
+ *                               rank calls vexb_comm_create_rank
+ * ---------------------------------------------------------------------- */
+typedef struct vexb_comm vexb_comm;
+#define VEXB_UNIQUE_ID_BYTES 128
+int vexb_comm_unique_id(void *id128);
+int vexb_comm_create_rank(int dev, int nranks, int rank, const void *id128, vexb_comm **comm);
+int vexb_comm_create_all(int ndev, const int *devs, vexb_comm **comms /* ndev out */);
+int vexb_comm_destroy(vexb_comm *comm);
+int vexb_comm_rank(const vexb_comm *comm, int *rank, int *nranks, int *dev);
+/* In-place all-reduce of `count` values on each local device.  op: VEXB_SUM / VEXB_MAX / VEXB_MIN. */
+int vexb_comm_allreduce(int nlocal, vexb_comm *const *comms, void *const *bufs, void *const *streams,
+                        int count, int dtype, int op);
+int vexb_comm_barrier(int nlocal, vexb_comm *const *comms, void *const *streams);
+
+/* ------------------------------------------------------------------------
+ * Halo plan (host only; no GPU needed): who sends which x entries to whom.
+ * Input: column partition and, for every part d, the sorted unique list of
+ * global column ids outside [col_part[d], col_part[d+1]) referenced by the
+ * rows of part d (the `ghost_cols[d]` sets of spmat.hpp:300-316),
+ * concatenated, with ghost_off[d]..ghost_off[d+1] delimiting part d.
+ * ---------------------------------------------------------------------- */
+typedef struct vexb_halo_plan vexb_halo_plan;
+/* Ghost columns of one row strip: two-call pattern (out == NULL returns the count). */
+int vexb_strip_ghost_cols(size_t nrows, const void *ptr, int ptr_bytes, const void *col, int col_bytes,
+                          size_t col_begin, size_t col_end, int64_t *out, size_t *count);
+int vexb_halo_plan_create(int nparts, const size_t *col_part, const int64_t *ghost_cols,
+                          const size_t *ghost_off, vexb_halo_plan **plan);
+int vexb_halo_plan_destroy(vexb_halo_plan *plan);
+/* Reference-equivalent tables (spmat.hpp:319-371), for parity checks:
+ * cols_to_send: global sorted union (n_send_total entries) with the owner's
+ * col_part start subtracted; cidx: nparts+1 offsets into it. */
+int vexb_halo_plan_ref_sizes(const vexb_halo_plan *plan, size_t *n_send_total);
+int vexb_halo_plan_ref_tables(const vexb_halo_plan *plan, int64_t *cols_to_send, size_t *cidx);
+int vexb_halo_plan_ref_recv(const vexb_halo_plan *plan, int part, int64_t *cols_to_recv /* n_ghost(part) */);
+/* Pairwise form used by the exchange: for `part`, send_counts[p] values go to
+ * peer p (send_cols lists the local x indices, grouped by ascending p);
+ * recv_counts[p] values arrive from peer p and land contiguously, in
+ * ascending p order, in the ghost buffer (which is ordered like the sorted
+ * ghost list, exactly the renumbering of csr.inl:92-96). */
+int vexb_halo_plan_counts(const vexb_halo_plan *plan, int part, size_t *send_counts, size_t *recv_counts);
+int vexb_halo_plan_send_cols(const vexb_halo_plan *plan, int part, int64_t *send_cols);
+
+/* ------------------------------------------------------------------------
+ * Sparse strips (one device).  Input: host CSR with column ids already local
+ * to the strip's x (ptr[0] may be non-zero; it is subtracted).  Index width
+ * on the device is 32-bit whenever that is lossless.
+ * ---------------------------------------------------------------------- */
+typedef struct vexb_spmat vexb_spmat;
+typedef enum {
+    VEXB_FMT_AUTO = 0,  /* CSR row-block stream kernel unless ELL is clearly better */
+    VEXB_FMT_CSR = 1,   /* row-block CSR, tiles staged through shared memory by TMA bulk copies */
+    VEXB_FMT_HELL = 2   /* hybrid ELL + CSR tail, width by hybrid_ell.inl:66-114 */
+} vexb_spfmt;
+
+int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols,
+                    const void *ptr, int ptr_bytes, const void *col, int col_bytes,
+                    const void *val, int val_dtype, int fmt, vexb_spmat **out);
+int vexb_spmat_destroy(vexb_spmat *A);
+typedef struct {
+    size_t  nrows, ncols, nnz;
+    int32_t fmt;          /* VEXB_FMT_CSR or VEXB_FMT_HELL */
+    int32_t val_dtype;
+    size_t  ell_width, ell_pitch, csr_tail_nnz;   /* HELL only */
+    size_t  n_tiles, tile_nnz;                    /* CSR only  */
+    size_t  device_bytes;                         /* bytes of matrix data resident in HBM */
+} vexb_spmat_info;
+int vexb_spmat_get_info(const vexb_spmat *A, vexb_spmat_info *info);
+/* Copy the HELL arrays back (parity with hybrid_ell.inl:132-193); any pointer may be NULL. */
+int vexb_spmat_hell_download(const vexb_spmat *A, int32_t *ell_col, void *ell_val,
+                             int64_t *csr_ptr, int32_t *csr_col, void *csr_val);
+/* y (=|+=) alpha * A x     (csr.inl:188-209: append ? "+=" : "=") */
+int vexb_spmv(int dev, void *stream, const vexb_spmat *A, const void *x, void *y, double alpha, int append);
+
+/* ------------------------------------------------------------------------
+ * Distributed SpMat part: the slice of a vex::SpMat owned by one device
+ * (spmat.hpp:71-106 ctor body for one d, :120-185 apply).
+ * `col` holds GLOBAL column ids for the strip's rows, indexed by ptr values
+ * relative to ptr[0].
+ * ---------------------------------------------------------------------- */
+typedef struct vexb_dspmat vexb_dspmat;
+int vexb_dspmat_create(int dev, void *stream, int part, const vexb_halo_plan *plan,
+                       size_t nrows, const void *ptr, int ptr_bytes, const void *col, int col_bytes,
+                       const void *val, int val_dtype, int fmt, vexb_dspmat **out);
+int vexb_dspmat_destroy(vexb_dspmat *A);
+typedef struct {
+    size_t nrows, ncols_local, n_ghost, n_send, loc_nnz, rem_nnz;
+    vexb_spmat_info loc, rem;
+} vexb_dspmat_info;
+int vexb_dspmat_get_info(const vexb_dspmat *A, vexb_dspmat_info *info);
+/* Split tables back on the host for parity with csr.inl:70-112 (any pointer may be NULL). */
+int vexb_dspmat_download_split(const vexb_dspmat *A, int64_t *loc_ptr, int64_t *loc_col, void *loc_val,
+                               int64_t *rem_ptr, int64_t *rem_col, void *rem_val);
+void *vexb_dspmat_send_buffer(const vexb_dspmat *A);  /* device, n_send values  */
+void *vexb_dspmat_ghost_buffer(const vexb_dspmat *A); /* device, n_ghost values */
+/* Steps of SpMat::apply, all asynchronous on `stream`: */
+int vexb_dspmat_pack(const vexb_dspmat *A, void *stream, const void *x);                       /* spmat.hpp:127-135 */
+int vexb_dspmat_mul_local(const vexb_dspmat *A, void *stream, const void *x, void *y, double alpha, int append); /* :142-146 */
+int vexb_dspmat_mul_remote(const vexb_dspmat *A, void *stream, void *y, double alpha);         /* :178-183 */
+/* Halo exchange for the local parts (grouped ncclSend/ncclRecv): send buffers -> peers' ghost buffers.
+ * Replaces spmat.hpp:149-176. */
+int vexb_halo_exchange(int nlocal, vexb_comm *const *comms, vexb_dspmat *const *parts, void *const *streams);
+/* Whole apply for the local parts: pack -> (side stream: exchange) || mul_local -> mul_remote.
+ * x[k], y[k] are the device slices of part k.  comms may be NULL when there are no ghosts. */
+int vexb_dspmat_apply(int nlocal, vexb_comm *const *comms, vexb_dspmat *const *parts, void *const *streams,
+                      const void *const *x, void *const *y, double alpha, int append);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VEXB200_H */

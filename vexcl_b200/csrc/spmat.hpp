@@ -1,0 +1,28 @@
+// Device-resident sparse strip (internal layout shared by spmv.cu and dspmat.cu).
+#pragma once
+#include "hostlogic.hpp"
+#include <vector>
+
+struct vexb_spmat {
+    int dev = 0;
+    int fmt = VEXB_FMT_CSR;
+    int val_dtype = VEXB_F64;
+    size_t nrows = 0, ncols = 0, nnz = 0;
+    // CSR stream
+    void *val = nullptr; int *col = nullptr; int *rowptr = nullptr; int2 *tile = nullptr;
+    size_t n_tiles = 0, tile_nnz = 0, tile_rows = 0;
+    // HELL
+    size_t ell_width = 0, ell_pitch = 0, tail_nnz = 0;
+    int *ell_col = nullptr; void *ell_val = nullptr;
+    int *tail_ptr = nullptr; int *tail_col = nullptr; void *tail_val = nullptr;
+    int *row_ids = nullptr;        // optional: compressed rows, y index of stored row r (remote strips)
+    size_t nrows_stored = 0;       // rows held in the arrays (== nrows unless row_ids)
+    size_t device_bytes = 0;
+};
+
+namespace vexb {
+// Build a strip from 32-bit host CSR.  row_ids (optional) maps stored row r to its y index;
+// nrows is then the length of y and rowptr.size()-1 the number of stored rows.
+int spmat_from_csr(int dev, size_t nrows, size_t ncols, std::vector<int> &rowptr, std::vector<int> &col,
+                   const void *val, int val_dtype, int fmt, const std::vector<int> *row_ids, vexb_spmat **out);
+}

@@ -1,0 +1,389 @@
+// Sparse strips on one device: y (=|+=) alpha * A * x.
+//
+// Replaces SpMatCSR / SpMatHELL (vexcl/spmat/csr.inl:45-209,
+// vexcl/spmat/hybrid_ell.inl:53-330): one thread per row, 8-byte indices,
+// row-strided (uncoalesced) val/col reads in the CSR case.
+//
+// CSR here is a row-block *stream* kernel:
+//   * rows are cut on the host into tiles of <= tile_nnz nonzeros / <= tile_rows rows;
+//   * one CTA per tile; an elected thread issues three TMA bulk copies
+//     (cp.async.bulk.shared.global -> UBLKCP) that stage the tile's row_ptr, col
+//     and val slices in shared memory and complete on an mbarrier;
+//   * phase A: all threads walk the staged nonzeros (coalesced), gather x[col]
+//     through L1/L2 and overwrite val in place with the product;
+//   * phase B: one thread per row adds its products in storage order -- the same
+//     sequential order as the reference kernel (csr.inl:163-170) -- or, for
+//     tiles with long rows, one warp per row with a shuffle tree;
+//   * rows longer than a tile are handled by a whole CTA straight from HBM.
+// Indices are 32-bit on the device (always lossless after the per-strip
+// renumbering, csr.inl:92-107), halving index traffic against SpMat<double>'s
+// default size_t (spmat.hpp:56).
+//
+// HELL keeps the reference layout (column-major ELL with pitch alignup(n,16),
+// sentinel column -1, CSR tail; hybrid_ell.inl:60,139-144,252-268) with 32-bit
+// columns, and unrolls the ELL loop for the common small widths.
+#include "spmat.hpp"
+#include <algorithm>
+
+
+namespace vexb {
+
+template <class T> __device__ __forceinline__ T t_mul(T a, T b);
+template <> __device__ __forceinline__ double t_mul<double>(double a, double b) { return __dmul_rn(a, b); }
+template <> __device__ __forceinline__ float t_mul<float>(float a, float b) { return __fmul_rn(a, b); }
+template <class T> __device__ __forceinline__ T t_add(T a, T b);
+template <> __device__ __forceinline__ double t_add<double>(double a, double b) { return __dadd_rn(a, b); }
+template <> __device__ __forceinline__ float t_add<float>(float a, float b) { return __fadd_rn(a, b); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class T>
+__device__ __forceinline__ void store_y(T *y, size_t r, T sum, T alpha, int append) {
+    const T v = t_mul<T>(alpha, sum);
+    y[r] = append ? t_add<T>(y[r], v) : v;
+}
+
+// Shared-memory carve-up (dynamic): [val: (tile_nnz+8)*sizeof(T)] [col: (tile_nnz+8)*4] [rp: (tile_rows+12)*4] [mbarrier]
+template <class T>
+__global__ void __launch_bounds__(256) csr_stream_kernel(const int2 *__restrict__ tile, const int *__restrict__ rowptr,
+                                                          const int *__restrict__ col, const T *__restrict__ val,
+                                                          const T *__restrict__ x, T *y, T alpha, int append,
+                                                          int tile_nnz, int tile_rows, const int *__restrict__ row_ids) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    T *val_s = reinterpret_cast<T *>(smem);
+    int *col_s = reinterpret_cast<int *>(smem + (size_t)(tile_nnz + 8) * sizeof(T));
+    int *rp_s = col_s + (tile_nnz + 8);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(rp_s + (tile_rows + 12));
+
+    const int2 t0 = tile[blockIdx.x], t1 = tile[blockIdx.x + 1];
+    const int r0 = t0.x, nr = t1.x - t0.x;
+    const int j0 = t0.y, cnt = t1.y - t0.y;
+    if (nr <= 0) return;
+
+    if (cnt > tile_nnz) {
+        // one long row: the whole CTA strides over it straight from global memory
+        T s = T(0);
+        for (int j = j0 + threadIdx.x; j < j0 + cnt; j += blockDim.x) s = t_add<T>(s, t_mul<T>(val[j], x[col[j]]));
+        __shared__ T red[8];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s = t_add<T>(s, __shfl_down_sync(0xffffffffu, s, off));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T tot = red[0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) tot = t_add<T>(tot, red[w]);
+            store_y<T>(y, row_ids ? (size_t)row_ids[r0] : (size_t)r0, tot, alpha, append);
+        }
+        return;
+    }
+
+    // aligned windows for the bulk copies (16-byte granularity)
+    const int j0a = j0 & ~3, j1a = (j0 + cnt + 3) & ~3;
+    const int r0a = r0 & ~3, r1a = (r0 + nr + 1 + 3) & ~3;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bv = (uint32_t)(j1a - j0a) * (uint32_t)sizeof(T);
+        const uint32_t bc = (uint32_t)(j1a - j0a) * 4u;
+        const uint32_t br = (uint32_t)(r1a - r0a) * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bv + bc + br) : "memory");
+        if (bv) { bulk_g2s(val_s, val + j0a, bv, bar); bulk_g2s(col_s, col + j0a, bc, bar); }
+        bulk_g2s(rp_s, rowptr + r0a, br, bar);
+    }
+    __syncthreads();   // barrier init visible to all waiters
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_u32(bar)), "r"(0u) : "memory");
+        }
+    }
+    // phase A: products in place
+    const int lo = j0 - j0a;
+    for (int j = lo + threadIdx.x; j < lo + cnt; j += blockDim.x) val_s[j] = t_mul<T>(val_s[j], __ldg(x + col_s[j]));
+    __syncthreads();
+    // phase B
+    const int *rp = rp_s + (r0 - r0a);
+    if (cnt <= 12 * nr) {
+        for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+            const int a = rp[r] - j0a, b = rp[r + 1] - j0a;
+            T s = T(0);
+            for (int j = a; j < b; ++j) s = t_add<T>(s, val_s[j]);
+            store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, s, alpha, append);
+        }
+    } else {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int r = warp; r < nr; r += nw) {
+            const int a = rp[r] - j0a, b = rp[r + 1] - j0a;
+            T s = T(0);
+            for (int j = a + lane; j < b; j += 32) s = t_add<T>(s, val_s[j]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s = t_add<T>(s, __shfl_down_sync(0xffffffffu, s, off));
+            if (lane == 0) store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, s, alpha, append);
+        }
+    }
+}
+
+template <class T, int W>
+__global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w_dyn, const int *__restrict__ ell_col,
+                                                    const T *__restrict__ ell_val, const int *__restrict__ tail_ptr,
+                                                    const int *__restrict__ tail_col, const T *__restrict__ tail_val,
+                                                    const T *__restrict__ x, T *y, T alpha, int append,
+                                                    const int *__restrict__ row_ids) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T sum = T(0);
+    if (W > 0) {
+        int c[W > 0 ? W : 1]; T v[W > 0 ? W : 1];
+#pragma unroll
+        for (int j = 0; j < W; ++j) { c[j] = __ldg(ell_col + i + (size_t)j * pitch); v[j] = __ldg(ell_val + i + (size_t)j * pitch); }
+#pragma unroll
+        for (int j = 0; j < W; ++j) if (c[j] != -1) sum = t_add<T>(sum, t_mul<T>(v[j], __ldg(x + c[j])));
+    } else {
+        for (int j = 0; j < w_dyn; ++j) {
+            const int c = __ldg(ell_col + i + (size_t)j * pitch);
+            if (c != -1) sum = t_add<T>(sum, t_mul<T>(__ldg(ell_val + i + (size_t)j * pitch), __ldg(x + c)));
+        }
+    }
+    if (tail_ptr) {
+        for (int j = tail_ptr[i], e = tail_ptr[i + 1]; j < e; ++j) sum = t_add<T>(sum, t_mul<T>(tail_val[j], __ldg(x + tail_col[j])));
+    }
+    store_y<T>(y, row_ids ? (size_t)row_ids[i] : i, sum, alpha, append);
+}
+
+template <class T>
+__global__ void zero_or_keep_kernel(T *y, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = T(0);
+}
+
+template <class T>
+static int upload(std::vector<T> &h, size_t pad, void **d, size_t *bytes_acc) {
+    const size_t n = h.size() + pad;
+    *d = nullptr;
+    if (n == 0) return VEXB_OK;
+    VEXB_CUDA(cudaMalloc(d, n * sizeof(T)));
+    if (pad) VEXB_CUDA(cudaMemset((char *)*d + h.size() * sizeof(T), 0, pad * sizeof(T)));
+    if (!h.empty()) VEXB_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *bytes_acc += n * sizeof(T);
+    return VEXB_OK;
+}
+
+// Width of the ELL part: smallest w such that the rows wider than w are fewer
+// than n/3 (ELL assumed 3x faster than CSR; hybrid_ell.inl:66-113).
+static size_t hell_width(const std::vector<int> &rowptr, size_t n) {
+    size_t maxw = 0;
+    for (size_t i = 0; i < n; ++i) maxw = std::max(maxw, (size_t)(rowptr[i + 1] - rowptr[i]));
+    std::vector<size_t> hist(maxw + 1, 0);
+    for (size_t i = 0; i < n; ++i) ++hist[rowptr[i + 1] - rowptr[i]];
+    size_t rows = n;
+    for (size_t w = 0; w < maxw; ++w) {
+        rows -= hist[w];                 // rows wider than w
+        if (3.0 * rows < n) return w;
+    }
+    return maxw;
+}
+
+template <class T>
+static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col, std::vector<T> &val, int fmt) {
+    const size_t n = A->nrows_stored;
+    if (fmt == VEXB_FMT_AUTO) {
+        // ELL when padding is small; otherwise the CSR stream kernel.
+        const size_t w = hell_width(rowptr, n);
+        size_t tail = 0;
+        for (size_t i = 0; i < n; ++i) { const size_t rw = rowptr[i + 1] - rowptr[i]; if (rw > w) tail += rw - w; }
+        const double padded = (double)w * (double)((n + 15) / 16 * 16) + (double)tail;
+        fmt = (A->nnz > 0 && padded <= 1.1 * (double)A->nnz && tail == 0) ? VEXB_FMT_HELL : VEXB_FMT_CSR;
+    }
+    A->fmt = fmt;
+    if (fmt == VEXB_FMT_CSR) {
+        long tn = param("spmv.tile_nnz", 2048), tr = param("spmv.tile_rows", 512);
+        tn = std::max(64l, std::min(tn, 8192l)) & ~3l;
+        tr = std::max(32l, std::min(tr, 4096l)) & ~3l;
+        A->tile_nnz = tn; A->tile_rows = tr;
+        std::vector<int2> tiles;
+        size_t r = 0;
+        while (r < n) {
+            size_t e = r; const int j0 = rowptr[r];
+            while (e < n && e - r < (size_t)tr && rowptr[e + 1] - j0 <= tn) ++e;
+            if (e == r) e = r + 1;        // a single row longer than a tile
+            tiles.push_back(make_int2((int)r, j0));
+            r = e;
+        }
+        tiles.push_back(make_int2((int)n, rowptr[n]));
+        A->n_tiles = tiles.size() - 1;
+        VEXB_TRY(upload(tiles, 0, (void **)&A->tile, &A->device_bytes));
+        VEXB_TRY(upload(rowptr, 16, (void **)&A->rowptr, &A->device_bytes));
+        VEXB_TRY(upload(col, 16, (void **)&A->col, &A->device_bytes));
+        VEXB_TRY(upload(val, 16, &A->val, &A->device_bytes));
+    } else {
+        const size_t w = hell_width(rowptr, n);
+        const size_t pitch = (n + 15) / 16 * 16;            // alignup(n, 16): hybrid_ell.inl:60
+        A->ell_width = w; A->ell_pitch = pitch;
+        std::vector<int> ecol(pitch * w, -1);               // sentinel (col_t)(-1): hybrid_ell.inl:139
+        std::vector<T> eval(pitch * w, T(0));
+        std::vector<int> tptr(n + 1, 0), tcol; std::vector<T> tval;
+        for (size_t i = 0; i < n; ++i) {
+            size_t cntw = 0;
+            for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+                if (cntw < w) { ecol[i + pitch * cntw] = col[j]; eval[i + pitch * cntw] = val[j]; ++cntw; }
+                else { tcol.push_back(col[j]); tval.push_back(val[j]); }
+            }
+            tptr[i + 1] = (int)tcol.size();
+        }
+        A->tail_nnz = tcol.size();
+        VEXB_TRY(upload(ecol, 0, (void **)&A->ell_col, &A->device_bytes));
+        VEXB_TRY(upload(eval, 0, &A->ell_val, &A->device_bytes));
+        if (A->tail_nnz) {
+            VEXB_TRY(upload(tptr, 0, (void **)&A->tail_ptr, &A->device_bytes));
+            VEXB_TRY(upload(tcol, 0, (void **)&A->tail_col, &A->device_bytes));
+            VEXB_TRY(upload(tval, 0, &A->tail_val, &A->device_bytes));
+        }
+    }
+    return VEXB_OK;
+}
+
+template <class T>
+static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T alpha, int append) {
+    if (A->nrows == 0) return VEXB_OK;
+    if (A->row_ids && !append) VEXB_FAIL(VEXB_ERR_INVALID, "row-compressed strips only support y += alpha*A*x");
+    if (A->nnz == 0) {
+        // y = A*x with an empty strip must still zero y (csr.inl:195-200)
+        if (!append) { zero_or_keep_kernel<T><<<(unsigned)((A->nrows + 255) / 256), 256, 0, st>>>(y, A->nrows); VEXB_LAUNCHED(); }
+        return VEXB_OK;
+    }
+    const size_t n = A->nrows_stored;
+    if (A->fmt == VEXB_FMT_CSR) {
+        const size_t smem = (A->tile_nnz + 8) * sizeof(T) + (A->tile_nnz + 8) * 4 + (A->tile_rows + 12) * 4 + 16;
+        static bool attr_set[2] = {false, false};
+        const int ti = sizeof(T) == 8 ? 0 : 1;
+        if (smem > 48 * 1024 && !attr_set[ti]) {
+            VEXB_CUDA(cudaFuncSetAttribute(csr_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[ti] = true;
+        }
+        csr_stream_kernel<T><<<(unsigned)A->n_tiles, 256, smem, st>>>(A->tile, A->rowptr, A->col, (const T *)A->val, x, y, alpha, append,
+                                                                     (int)A->tile_nnz, (int)A->tile_rows, A->row_ids);
+        VEXB_LAUNCHED();
+    } else {
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+#define HL(W) hell_kernel<T, W><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col, (const T *)A->ell_val, \
+                  A->tail_ptr, A->tail_col, (const T *)A->tail_val, x, y, alpha, append, A->row_ids)
+        switch (A->ell_width) {
+            case 1: HL(1); break; case 2: HL(2); break; case 3: HL(3); break; case 4: HL(4); break;
+            case 5: HL(5); break; case 6: HL(6); break; case 7: HL(7); break; case 8: HL(8); break;
+            case 9: HL(9); break;
+            default: HL(0); break;
+        }
+#undef HL
+        VEXB_LAUNCHED();
+    }
+    return VEXB_OK;
+}
+
+} // namespace vexb
+
+int vexb::spmat_from_csr(int dev, size_t nrows, size_t ncols, std::vector<int> &rowptr, std::vector<int> &col,
+                         const void *val, int val_dtype, int fmt, const std::vector<int> *row_ids, vexb_spmat **out) {
+    DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
+    auto *A = new vexb_spmat();
+    A->dev = dev; A->val_dtype = val_dtype; A->nrows = nrows; A->ncols = ncols;
+    A->nrows_stored = rowptr.size() - 1; A->nnz = (size_t)rowptr.back();
+    const size_t nnz = A->nnz;
+    int st = VEXB_OK;
+    if (val_dtype == VEXB_F64) { std::vector<double> v((const double *)val, (const double *)val + nnz); st = build<double>(A, rowptr, col, v, fmt); }
+    else { std::vector<float> v((const float *)val, (const float *)val + nnz); st = build<float>(A, rowptr, col, v, fmt); }
+    if (st == VEXB_OK && row_ids) {
+        std::vector<int> ids(*row_ids);
+        st = upload(ids, 0, (void **)&A->row_ids, &A->device_bytes);
+    }
+    if (st != VEXB_OK) { vexb_spmat_destroy(A); return st; }
+    *out = A;
+    return VEXB_OK;
+}
+
+using namespace vexb;
+
+extern "C" int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols,
+                               const void *ptr, int ptr_bytes, const void *col, int col_bytes,
+                               const void *val, int val_dtype, int fmt, vexb_spmat **out) {
+    (void)stream;
+    VEXB_CHECK(out, "out is NULL");
+    VEXB_CHECK(ptr_bytes == 4 || ptr_bytes == 8, "ptr_bytes must be 4 or 8");
+    VEXB_CHECK(col_bytes == 4 || col_bytes == 8, "col_bytes must be 4 or 8");
+    VEXB_CHECK(val_dtype == VEXB_F64 || val_dtype == VEXB_F32, "values must be f64 or f32");
+    VEXB_CHECK(fmt >= VEXB_FMT_AUTO && fmt <= VEXB_FMT_HELL, "bad format %d", fmt);
+    VEXB_CHECK(nrows == 0 || ptr, "ptr is NULL");
+    VEXB_CHECK(nrows < (size_t)INT32_MAX && ncols < (size_t)INT32_MAX, "strip dimensions exceed 32-bit local indices");
+    DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
+
+    const int64_t p0 = nrows ? read_index(ptr, ptr_bytes, 0) : 0;
+    const int64_t nnz = nrows ? read_index(ptr, ptr_bytes, nrows) - p0 : 0;
+    VEXB_CHECK(nnz >= 0 && nnz < (int64_t)INT32_MAX - 64, "strip nnz=%lld does not fit 32-bit row pointers", (long long)nnz);
+    VEXB_CHECK(nnz == 0 || (col && val), "col/val is NULL");
+
+    std::vector<int> rp(nrows + 1), c((size_t)nnz);
+    for (size_t i = 0; i <= nrows; ++i) {
+        rp[i] = nrows ? (int)(read_index(ptr, ptr_bytes, i) - p0) : 0;
+        VEXB_CHECK(i == 0 || rp[i] >= rp[i - 1], "row pointers decrease at row %zu", i);
+    }
+    for (size_t j = 0; j < (size_t)nnz; ++j) {
+        const int64_t cj = read_index(col, col_bytes, j);
+        VEXB_CHECK(cj >= 0 && (size_t)cj < ncols, "column %lld out of range at nnz %zu", (long long)cj, j);
+        c[j] = (int)cj;
+    }
+    return spmat_from_csr(dev, nrows, ncols, rp, c, val, val_dtype, fmt, nullptr, out);
+}
+
+extern "C" int vexb_spmat_destroy(vexb_spmat *A) {
+    if (!A) return VEXB_OK;
+    DeviceGuard g(A->dev);
+    cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile);
+    cudaFree(A->row_ids); cudaFree(A->ell_col); cudaFree(A->ell_val); cudaFree(A->tail_ptr); cudaFree(A->tail_col); cudaFree(A->tail_val);
+    delete A;
+    return VEXB_OK;
+}
+
+extern "C" int vexb_spmat_get_info(const vexb_spmat *A, vexb_spmat_info *info) {
+    VEXB_CHECK(A && info, "NULL argument");
+    memset(info, 0, sizeof(*info));
+    info->nrows = A->nrows; info->ncols = A->ncols; info->nnz = A->nnz;
+    info->fmt = A->fmt; info->val_dtype = A->val_dtype;
+    info->ell_width = A->ell_width; info->ell_pitch = A->ell_pitch; info->csr_tail_nnz = A->tail_nnz;
+    info->n_tiles = A->n_tiles; info->tile_nnz = A->tile_nnz;
+    info->device_bytes = A->device_bytes;
+    return VEXB_OK;
+}
+
+extern "C" int vexb_spmat_hell_download(const vexb_spmat *A, int32_t *ell_col, void *ell_val,
+                                        int64_t *csr_ptr, int32_t *csr_col, void *csr_val) {
+    VEXB_CHECK(A && A->fmt == VEXB_FMT_HELL, "not a HELL matrix");
+    DeviceGuard g(A->dev);
+    const size_t vs = dtype_size(A->val_dtype), ne = A->ell_pitch * A->ell_width;
+    if (ell_col && ne) VEXB_CUDA(cudaMemcpy(ell_col, A->ell_col, ne * 4, cudaMemcpyDeviceToHost));
+    if (ell_val && ne) VEXB_CUDA(cudaMemcpy(ell_val, A->ell_val, ne * vs, cudaMemcpyDeviceToHost));
+    if (csr_ptr) {
+        if (A->tail_nnz) {
+            std::vector<int> tp(A->nrows_stored + 1);
+            VEXB_CUDA(cudaMemcpy(tp.data(), A->tail_ptr, tp.size() * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i <= A->nrows_stored; ++i) csr_ptr[i] = tp[i];
+        } else for (size_t i = 0; i <= A->nrows_stored; ++i) csr_ptr[i] = 0;
+    }
+    if (csr_col && A->tail_nnz) VEXB_CUDA(cudaMemcpy(csr_col, A->tail_col, A->tail_nnz * 4, cudaMemcpyDeviceToHost));
+    if (csr_val && A->tail_nnz) VEXB_CUDA(cudaMemcpy(csr_val, A->tail_val, A->tail_nnz * vs, cudaMemcpyDeviceToHost));
+    return VEXB_OK;
+}
+
+extern "C" int vexb_spmv(int dev, void *stream, const vexb_spmat *A, const void *x, void *y, double alpha, int append) {
+    VEXB_CHECK(A, "matrix is NULL");
+    VEXB_CHECK(dev == A->dev, "matrix lives on device %d, not %d", A->dev, dev);
+    VEXB_CHECK(A->nrows == 0 || y, "y is NULL");
+    VEXB_CHECK(A->nnz == 0 || x, "x is NULL");
+    DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
+    if (A->val_dtype == VEXB_F64) return spmv_launch<double>(A, (cudaStream_t)stream, (const double *)x, (double *)y, alpha, append);
+    return spmv_launch<float>(A, (cudaStream_t)stream, (const float *)x, (float *)y, (float)alpha, append);
+}

@@ -1,0 +1,76 @@
+"""Synthetic workloads of the named configurations, generated strip by strip.
+
+Matrix convention = the reference benchmark's (examples/benchmark.cpp:357-415): a regular
+grid, rows on the domain boundary are identity (col = idx, val = 1), interior rows carry the
+full 5-point (2-D) / 7-point (3-D) stencil with h2i = (n-1)^2 off-diagonal weight -h2i and
+diagonal 4*h2i / 6*h2i, columns in ascending order.  `poisson_strip` produces rows
+[r0, r1) only (global column ids, row offsets starting at 0), so that a rank never
+materialises more than its own slab.  Grids may be anisotropic (nx, ny, nz) for the weak
+scaling runs; h2i is always (nx-1)^2.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def poisson_dims(dim: int, nx: int, ny: int | None = None, nz: int | None = None):
+    ny = nx if ny is None else ny
+    nz = (nx if nz is None else nz) if dim == 3 else 1
+    return nx, ny, nz
+
+
+def poisson_strip(dim: int, nx: int, ny: int | None = None, nz: int | None = None, r0: int = 0, r1: int | None = None,
+                  index_dtype=np.int64):
+    """Rows [r0, r1) of the Poisson matrix on an nx*ny(*nz) grid.  Returns (row, col, val)."""
+    nx, ny, nz = poisson_dims(dim, nx, ny, nz)
+    N = nx * ny * nz
+    r1 = N if r1 is None else r1
+    idx = np.arange(r0, r1, dtype=np.int64)
+    i = idx % nx
+    j = (idx // nx) % ny
+    k = idx // (nx * ny)
+    bnd = (i == 0) | (i == nx - 1) | (j == 0) | (j == ny - 1)
+    if dim == 3:
+        bnd |= (k == 0) | (k == nz - 1)
+    h2i = float((nx - 1) * (nx - 1))
+    if dim == 2:
+        offs = np.array([-nx, -1, 0, 1, nx], dtype=np.int64)
+        vals = np.array([-h2i, -h2i, 4 * h2i, -h2i, -h2i])
+    else:
+        offs = np.array([-nx * ny, -nx, -1, 0, 1, nx, nx * ny], dtype=np.int64)
+        vals = np.array([-h2i, -h2i, -h2i, 6 * h2i, -h2i, -h2i, -h2i])
+    w = offs.size
+    width = np.where(bnd, 1, w).astype(np.int64)
+    row = np.zeros(idx.size + 1, dtype=np.int64)
+    np.cumsum(width, out=row[1:])
+    nnz = int(row[-1])
+    col = np.empty(nnz, dtype=np.int64)
+    val = np.empty(nnz, dtype=np.float64)
+    # boundary rows
+    b_at = row[:-1][bnd]
+    col[b_at] = idx[bnd]
+    val[b_at] = 1.0
+    # interior rows
+    inner = ~bnd
+    i_at = row[:-1][inner]
+    i_idx = idx[inner]
+    for t in range(w):
+        col[i_at + t] = i_idx + offs[t]
+        val[i_at + t] = vals[t]
+    return row.astype(index_dtype), col.astype(index_dtype), val
+
+
+def poisson_nnz(dim: int, nx: int, ny: int | None = None, nz: int | None = None) -> tuple[int, int]:
+    nx, ny, nz = poisson_dims(dim, nx, ny, nz)
+    N = nx * ny * nz
+    if dim == 2:
+        inner = max(nx - 2, 0) * max(ny - 2, 0)
+        return N, inner * 5 + (N - inner)
+    inner = max(nx - 2, 0) * max(ny - 2, 0) * max(nz - 2, 0)
+    return N, inner * 7 + (N - inner)
+
+
+def spmv_bytes(nrows: int, ncols: int, nnz: int, append: bool = False) -> int:
+    """Algorithmic bytes of y = A*x: double values, 32-bit columns and row
+    pointers, x and y touched once; + nrows*8 for y += A*x."""
+    return nnz * 12 + (nrows + 1) * 4 + ncols * 8 + nrows * 8 + (nrows * 8 if append else 0)
