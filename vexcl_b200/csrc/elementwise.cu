@@ -173,7 +173,7 @@ using namespace vexb;
 extern "C" int vexb_eval_path(int lhs_dtype, int assign_op, const vexb_expr *expr, char *buf, size_t buflen) {
     VEXB_CHECK(buf && buflen > 0, "bad buffer");
     vexb_expr e;
-    VEXB_TRY(normalize_expr(expr, &e));
+    VEXB_TRY(normalize_expr(expr, &e, false));
     ShapeMatch m; SweepArgs a;
     // alignment is checked on the real pointers too: a 32-byte aligned dummy lhs stands in here
     alignas(32) static char dummy[32];
@@ -187,7 +187,7 @@ extern "C" int vexb_eval(int dev, void *stream, void *lhs, int lhs_dtype, int as
     VEXB_CHECK(lhs_dtype >= VEXB_F64 && lhs_dtype <= VEXB_U64, "bad lhs dtype %d", lhs_dtype);
     VEXB_CHECK(assign_op >= VEXB_SET && assign_op <= VEXB_RSH, "bad assign op %d", assign_op);
     vexb_expr e;
-    VEXB_TRY(normalize_expr(expr, &e));
+    VEXB_TRY(normalize_expr(expr, &e, n != 0));
     if (n == 0) return VEXB_OK;                    // empty partitions are legal (operations.hpp:1886)
     VEXB_CHECK(lhs != nullptr, "lhs is NULL");
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);

@@ -79,7 +79,7 @@ inline int host_result_type(const vexb_expr &e) {
 }
 
 // Validate `in` and write the normalised program to `out`.
-inline int normalize_expr(const vexb_expr *in, vexb_expr *out) {
+inline int normalize_expr(const vexb_expr *in, vexb_expr *out, bool need_ptrs = true) {
     VEXB_CHECK(in && out, "expression is NULL");
     VEXB_CHECK(in->n_terms >= 0 && in->n_terms <= VEXB_MAX_TERMS, "n_terms=%d out of range", in->n_terms);
     VEXB_CHECK(in->n_code >= 1 && in->n_code <= VEXB_MAX_CODE, "n_code=%d out of range", in->n_code);
@@ -87,7 +87,7 @@ inline int normalize_expr(const vexb_expr *in, vexb_expr *out) {
         const vexb_term &t = in->term[k];
         VEXB_CHECK(t.kind <= VEXB_TERM_INDEX, "term %d: bad kind %d", k, (int)t.kind);
         VEXB_CHECK(t.dtype <= VEXB_U64, "term %d: bad dtype %d", k, (int)t.dtype);
-        VEXB_CHECK(t.kind != VEXB_TERM_VEC || t.v.ptr != nullptr, "term %d: NULL device pointer", k);
+        VEXB_CHECK(!need_ptrs || t.kind != VEXB_TERM_VEC || t.v.ptr != nullptr, "term %d: NULL device pointer", k);
     }
     // 1. de-duplicate vector terminals (same pointer, same dtype) and drop unused ones.
     int remap[VEXB_MAX_TERMS];

@@ -276,7 +276,7 @@ extern "C" int vexb_reduce(int dev, void *stream, const vexb_expr *expr, int dty
     VEXB_CHECK(d_result && d_workspace, "d_result / d_workspace is NULL");
     if (op == VEXB_SUM_KAHAN && !dtype_is_float(dtype)) op = VEXB_SUM;
     vexb_expr e;
-    VEXB_TRY(normalize_expr(expr, &e));
+    VEXB_TRY(normalize_expr(expr, &e, n != 0));
     if (n == 0) return vexb_reduce_identity(dev, stream, dtype, op, d_result);   // reductor.hpp:318-321
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     cudaStream_t st = (cudaStream_t)stream;
