@@ -202,7 +202,7 @@ extern "C" int vexb_eval(int dev, void *stream, void *lhs, int lhs_dtype, int as
         size_t want = (nvec + per_block - 1) / per_block;
         if (want < 1) want = 1;
         const long bps = param("sweep.blocks_per_sm", 8);
-        size_t cap = param("sweep.persistent", 1) ? (size_t)sms * (size_t)bps : want;
+        size_t cap = param("sweep.persistent", 0) ? (size_t)sms * (size_t)bps : want;
         int blocks = (int)(want < cap ? want : cap);
         if (lhs_dtype == VEXB_F64) launch_sweep_shape<double>(m.shape, assign_op, blocks, st, lhs, a, n);
         else                       launch_sweep_shape<float>(m.shape, assign_op, blocks, st, lhs, a, n);

@@ -37,15 +37,64 @@ template <> __device__ __forceinline__ float t_add<float>(float a, float b) { re
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// L2 residency control.  The matrix streams through once per product, x is gathered ~nnz/ncols
+// times: matrix traffic is marked evict-first and x evict-last, so the stream does not push x out
+// of the 126 MB L2 (x gathers that miss L1 then cost an L2 hit, not an HBM round trip).
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+__device__ __forceinline__ double ldg_keep(const double *p, uint64_t policy) {
+    double v; asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy)); return v;
+}
+__device__ __forceinline__ float ldg_keep(const float *p, uint64_t policy) {
+    float v; asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy)); return v;
+}
+__device__ __forceinline__ int ldg_stream(const int *p, uint64_t policy) {
+    int v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy)); return v;
+}
+__device__ __forceinline__ double ldg_stream(const double *p, uint64_t policy) {
+    double v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy)); return v;
+}
+__device__ __forceinline__ float ldg_stream(const float *p, uint64_t policy) {
+    float v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy)); return v;
 }
 
 template <class T>
 __device__ __forceinline__ void store_y(T *y, size_t r, T sum, T alpha, int append) {
     const T v = t_mul<T>(alpha, sum);
     y[r] = append ? t_add<T>(y[r], v) : v;
+}
+
+// Phase A of the stream kernels: val_s[j] *= x[col_s[j]] for j in [lo, lo+cnt), all threads.
+// The gathers of a batch are issued before any product is stored, so a thread keeps UA
+// independent L1/L2 requests in flight (a plain loop would serialise on the in-place store).
+template <class T, int UA>
+__device__ __forceinline__ void phase_a_products(T *val_s, const int *col_s, const T *__restrict__ x,
+                                                 int lo, int cnt, int tid, int nthreads) {
+    const uint64_t keep = l2_policy_keep();
+    const int hi = lo + cnt;
+    for (int j = lo + tid; j < hi; j += nthreads * UA) {
+        T xv[UA];
+#pragma unroll
+        for (int u = 0; u < UA; ++u) {
+            const int jj = j + u * nthreads;
+            xv[u] = (jj < hi) ? ldg_keep(x + col_s[jj], keep) : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < UA; ++u) {
+            const int jj = j + u * nthreads;
+            if (jj < hi) val_s[jj] = t_mul<T>(val_s[jj], xv[u]);
+        }
+    }
 }
 
 // Shared-memory carve-up (dynamic): [val: (tile_nnz+8)*sizeof(T)] [col: (tile_nnz+8)*4] [rp: (tile_rows+12)*4] [mbarrier]
@@ -92,8 +141,9 @@ __global__ void __launch_bounds__(256) csr_stream_kernel(const int2 *__restrict_
         const uint32_t bc = (uint32_t)(j1a - j0a) * 4u;
         const uint32_t br = (uint32_t)(r1a - r0a) * 4u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bv + bc + br) : "memory");
-        if (bv) { bulk_g2s(val_s, val + j0a, bv, bar); bulk_g2s(col_s, col + j0a, bc, bar); }
-        bulk_g2s(rp_s, rowptr + r0a, br, bar);
+        const uint64_t stream = l2_policy_stream();
+        if (bv) { bulk_g2s(val_s, val + j0a, bv, bar, stream); bulk_g2s(col_s, col + j0a, bc, bar, stream); }
+        bulk_g2s(rp_s, rowptr + r0a, br, bar, stream);
     }
     __syncthreads();   // barrier init visible to all waiters
     {
@@ -105,7 +155,7 @@ __global__ void __launch_bounds__(256) csr_stream_kernel(const int2 *__restrict_
     }
     // phase A: products in place
     const int lo = j0 - j0a;
-    for (int j = lo + threadIdx.x; j < lo + cnt; j += blockDim.x) val_s[j] = t_mul<T>(val_s[j], __ldg(x + col_s[j]));
+    phase_a_products<T, 8>(val_s, col_s, x, lo, cnt, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
     // phase B
     const int *rp = rp_s + (r0 - r0a);
@@ -129,6 +179,138 @@ __global__ void __launch_bounds__(256) csr_stream_kernel(const int2 *__restrict_
     }
 }
 
+// ---- persistent, warp-specialised, multi-stage version of the stream kernel ---------------------
+// One producer warp keeps up to `stages` tiles in flight with TMA bulk copies (full/empty
+// mbarrier ring); eight consumer warps do phase A / phase B of the oldest tile meanwhile, so
+// HBM never waits for the gather or the row sums.  Grid = resident CTAs only; tiles are dealt
+// round-robin (tile = blockIdx.x + it * gridDim.x).
+constexpr int kPipeConsumers = 256;
+constexpr int kPipeThreads = kPipeConsumers + 32;
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kPipeThreads) csr_pipe_kernel(const int2 *__restrict__ tile, int n_tiles,
+                                                                 const int *__restrict__ rowptr, const int *__restrict__ col,
+                                                                 const T *__restrict__ val, const T *__restrict__ x, T *y,
+                                                                 T alpha, int append, int tile_nnz, int tile_rows, int stages,
+                                                                 const int *__restrict__ row_ids) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const size_t val_bytes = (size_t)(tile_nnz + 8) * sizeof(T);
+    const size_t col_bytes = (size_t)(tile_nnz + 8) * 4;
+    const size_t rp_bytes = (size_t)(tile_rows + 12) * 4;
+    const size_t stage_bytes = (val_bytes + col_bytes + rp_bytes + 127) & ~(size_t)127;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + stage_bytes * stages);
+    uint64_t *empty = full + stages;
+    int4 *meta = reinterpret_cast<int4 *>(empty + stages);          // per stage: {r0, nr, j0, cnt}
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(full + s)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(empty + s)), "r"(kPipeConsumers / 32) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kPipeConsumers / 32) {
+        // ===== producer warp (one elected lane) =====
+        if (lane == 0) {
+            const uint64_t stream = l2_policy_stream();
+            int it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const int s = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                mbar_wait(empty + s, ph ^ 1u);                       // slot free (passes at once on the first lap)
+                const int2 t0 = __ldg(tile + t), t1 = __ldg(tile + t + 1);
+                const int r0 = t0.x, nr = t1.x - t0.x, j0 = t0.y, cnt = t1.y - t0.y;
+                meta[s] = make_int4(r0, nr, j0, cnt);
+                unsigned char *base = smem + stage_bytes * s;
+                if (cnt > tile_nnz || nr <= 0) {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(full + s)) : "memory");
+                    continue;
+                }
+                const int j0a = j0 & ~3, j1a = (j0 + cnt + 3) & ~3;
+                const int r0a = r0 & ~3, r1a = (r0 + nr + 1 + 3) & ~3;
+                const uint32_t bv = (uint32_t)(j1a - j0a) * (uint32_t)sizeof(T);
+                const uint32_t bc = (uint32_t)(j1a - j0a) * 4u;
+                const uint32_t br = (uint32_t)(r1a - r0a) * 4u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(full + s)), "r"(bv + bc + br) : "memory");
+                if (bv) { bulk_g2s(base, val + j0a, bv, full + s, stream); bulk_g2s(base + val_bytes, col + j0a, bc, full + s, stream); }
+                bulk_g2s(base + val_bytes + col_bytes, rowptr + r0a, br, full + s, stream);
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    const int tid = threadIdx.x;                                      // 0 .. 255
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        mbar_wait(full + s, ph);
+        const int4 m = meta[s];
+        const int r0 = m.x, nr = m.y, j0 = m.z, cnt = m.w;
+        unsigned char *base = smem + stage_bytes * s;
+        T *val_s = reinterpret_cast<T *>(base);
+        const int *col_s = reinterpret_cast<const int *>(base + val_bytes);
+        const int *rp_s = reinterpret_cast<const int *>(base + val_bytes + col_bytes);
+        if (nr > 0 && cnt > tile_nnz) {
+            // one long row, straight from global memory, reduced across the consumer warps
+            T sacc = T(0);
+            for (int j = j0 + tid; j < j0 + cnt; j += kPipeConsumers) sacc = t_add<T>(sacc, t_mul<T>(val[j], __ldg(x + col[j])));
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sacc = t_add<T>(sacc, __shfl_down_sync(0xffffffffu, sacc, off));
+            T *red = val_s;                                           // the stage is unused for this tile
+            if (lane == 0) red[warp] = sacc;
+            asm volatile("bar.sync 1, %0;" :: "n"(kPipeConsumers) : "memory");
+            if (tid == 0) {
+                T tot = red[0];
+                for (int w = 1; w < kPipeConsumers / 32; ++w) tot = t_add<T>(tot, red[w]);
+                store_y<T>(y, row_ids ? (size_t)row_ids[r0] : (size_t)r0, tot, alpha, append);
+            }
+            asm volatile("bar.sync 1, %0;" :: "n"(kPipeConsumers) : "memory");
+        } else if (nr > 0) {
+            const int j0a = j0 & ~3, r0a = r0 & ~3;
+            const int lo = j0 - j0a;
+            // phase A: products in place (coalesced walk over the staged nonzeros, x gathered through L1/L2)
+            phase_a_products<T, 8>(val_s, col_s, x, lo, cnt, tid, kPipeConsumers);
+            asm volatile("bar.sync 1, %0;" :: "n"(kPipeConsumers) : "memory");
+            // phase B: row sums in storage order
+            const int *rp = rp_s + (r0 - r0a);
+            if (cnt <= 12 * nr) {
+                for (int r = tid; r < nr; r += kPipeConsumers) {
+                    const int a = rp[r] - j0a, b = rp[r + 1] - j0a;
+                    T sacc = T(0);
+                    for (int j = a; j < b; ++j) sacc = t_add<T>(sacc, val_s[j]);
+                    store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, sacc, alpha, append);
+                }
+            } else {
+                for (int r = warp; r < nr; r += kPipeConsumers / 32) {
+                    const int a = rp[r] - j0a, b = rp[r + 1] - j0a;
+                    T sacc = T(0);
+                    for (int j = a + lane; j < b; j += 32) sacc = t_add<T>(sacc, val_s[j]);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) sacc = t_add<T>(sacc, __shfl_down_sync(0xffffffffu, sacc, off));
+                    if (lane == 0) store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, sacc, alpha, append);
+                }
+            }
+        }
+        // release the stage: generic-proxy accesses ordered before the next TMA write into it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(empty + s)) : "memory");
+    }
+}
+
 template <class T, int W>
 __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w_dyn, const int *__restrict__ ell_col,
                                                     const T *__restrict__ ell_val, const int *__restrict__ tail_ptr,
@@ -138,16 +320,19 @@ __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     T sum = T(0);
+    const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
     if (W > 0) {
-        int c[W > 0 ? W : 1]; T v[W > 0 ? W : 1];
+        int c[W > 0 ? W : 1]; T v[W > 0 ? W : 1]; T xv[W > 0 ? W : 1];
 #pragma unroll
-        for (int j = 0; j < W; ++j) { c[j] = __ldg(ell_col + i + (size_t)j * pitch); v[j] = __ldg(ell_val + i + (size_t)j * pitch); }
+        for (int j = 0; j < W; ++j) { c[j] = ldg_stream(ell_col + i + (size_t)j * pitch, stream); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
 #pragma unroll
-        for (int j = 0; j < W; ++j) if (c[j] != -1) sum = t_add<T>(sum, t_mul<T>(v[j], __ldg(x + c[j])));
+        for (int j = 0; j < W; ++j) xv[j] = (c[j] != -1) ? ldg_keep(x + c[j], keep) : T(0);
+#pragma unroll
+        for (int j = 0; j < W; ++j) if (c[j] != -1) sum = t_add<T>(sum, t_mul<T>(v[j], xv[j]));
     } else {
         for (int j = 0; j < w_dyn; ++j) {
-            const int c = __ldg(ell_col + i + (size_t)j * pitch);
-            if (c != -1) sum = t_add<T>(sum, t_mul<T>(__ldg(ell_val + i + (size_t)j * pitch), __ldg(x + c)));
+            const int c = ldg_stream(ell_col + i + (size_t)j * pitch, stream);
+            if (c != -1) sum = t_add<T>(sum, t_mul<T>(ldg_stream(ell_val + i + (size_t)j * pitch, stream), ldg_keep(x + c, keep)));
         }
     }
     if (tail_ptr) {
@@ -258,7 +443,28 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
         return VEXB_OK;
     }
     const size_t n = A->nrows_stored;
-    if (A->fmt == VEXB_FMT_CSR) {
+    if (A->fmt == VEXB_FMT_CSR && param("spmv.pipeline", 0)) {
+        long stages = param("spmv.stages", 4);
+        stages = std::max(2l, std::min(stages, 16l));
+        const size_t stage_bytes = ((A->tile_nnz + 8) * sizeof(T) + (A->tile_nnz + 8) * 4 + (A->tile_rows + 12) * 4 + 127) & ~(size_t)127;
+        size_t smem = stage_bytes * stages + 16 * stages + 16 * stages + 16;
+        while (smem > 220 * 1024 && stages > 2) { --stages; smem = stage_bytes * stages + 32 * stages + 16; }
+        static int attr_set[2] = {0, 0};
+        const int ti = sizeof(T) == 8 ? 0 : 1;
+        if (!attr_set[ti]) {
+            VEXB_CUDA(cudaFuncSetAttribute(csr_pipe_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            attr_set[ti] = 1;
+        }
+        int per_sm = 0;
+        VEXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_pipe_kernel<T>, kPipeThreads, smem));
+        if (per_sm < 1) VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "CSR tile of %zu nnz does not fit in shared memory", A->tile_nnz);
+        const long cap = param("spmv.ctas_per_sm", 0);
+        if (cap > 0 && per_sm > cap) per_sm = (int)cap;
+        const size_t grid = std::min(A->n_tiles, (size_t)per_sm * (size_t)sm_count(A->dev));
+        csr_pipe_kernel<T><<<(unsigned)grid, kPipeThreads, smem, st>>>(A->tile, (int)A->n_tiles, A->rowptr, A->col, (const T *)A->val, x, y,
+                                                                     alpha, append, (int)A->tile_nnz, (int)A->tile_rows, (int)stages, A->row_ids);
+        VEXB_LAUNCHED();
+    } else if (A->fmt == VEXB_FMT_CSR) {
         const size_t smem = (A->tile_nnz + 8) * sizeof(T) + (A->tile_nnz + 8) * 4 + (A->tile_rows + 12) * 4 + 16;
         static bool attr_set[2] = {false, false};
         const int ti = sizeof(T) == 8 ? 0 : 1;
