@@ -1,0 +1,106 @@
+#ifndef VEXCL_SPMAT_HPP
+#define VEXCL_SPMAT_HPP
+/*
+ * vex::SpMat<val_t, col_t, idx_t> (vexcl/spmat.hpp:56-386): CSR in, one row strip per device,
+ * ghost columns exchanged between devices, `y = A * x`, `y += A * x`, `y -= 2 * (A * x)`, ...
+ *
+ * What changed behind the same interface:
+ *   - strips are stored with 32-bit local indices and multiplied by hand-written sm_100a
+ *     kernels (row-block CSR stream with TMA staging, or hybrid ELL; libvexb200 picks);
+ *   - the ghost exchange (reference: D2H, host shuffle, H2D with three host syncs,
+ *     spmat.hpp:137-175) is grouped ncclSend/ncclRecv between device buffers on a side stream,
+ *     overlapped with the local product; nothing in apply() waits on the host.
+ */
+#include <memory>
+#include "reductor.hpp"
+#include "vector.hpp"
+
+namespace vex {
+
+template <typename val_t, typename col_t = size_t, typename idx_t = size_t>
+class SpMat {
+    public:
+        typedef val_t value_type;
+        typedef val_t scalar_type;
+
+        SpMat() : nrows(0), ncols(0), nnz(0), plan(nullptr) {}
+
+        SpMat(const std::vector<backend::command_queue> &queue, size_t n, size_t m,
+              const idx_t *row, const col_t *col, const val_t *val, int format = VEXB_FMT_AUTO)
+            : queue(queue), part(vex::partition(n, queue)), col_part(vex::partition(m, queue)),
+              nrows(n), ncols(m), nnz(row[n]), plan(nullptr), mtx(queue.size(), nullptr)
+        {
+            static_assert(sizeof(col_t) == 4 || sizeof(col_t) == 8, "column type must be 32 or 64 bit");
+            static_assert(sizeof(idx_t) == 4 || sizeof(idx_t) == 8, "index type must be 32 or 64 bit");
+            const int nd = static_cast<int>(queue.size());
+            // ghost columns of each strip (spmat.hpp:300-316)
+            std::vector<int64_t> ghosts; std::vector<size_t> off(nd + 1, 0);
+            for (int d = 0; d < nd; ++d) {
+                size_t cnt = 0;
+                if (nd > 1) {
+                    const size_t nloc = part[d + 1] - part[d];
+                    VEXB_CHECKED(vexb_strip_ghost_cols(nloc, row + part[d], sizeof(idx_t), col + row[part[d]], sizeof(col_t),
+                                                       col_part[d], col_part[d + 1], nullptr, &cnt));
+                    ghosts.resize(off[d] + cnt);
+                    size_t cap = cnt;
+                    VEXB_CHECKED(vexb_strip_ghost_cols(nloc, row + part[d], sizeof(idx_t), col + row[part[d]], sizeof(col_t),
+                                                       col_part[d], col_part[d + 1], ghosts.data() + off[d], &cap));
+                }
+                off[d + 1] = off[d] + cnt;
+            }
+            VEXB_CHECKED(vexb_halo_plan_create(nd, col_part.data(), ghosts.data(), off.data(), &plan));
+            for (int d = 0; d < nd; ++d) {
+                const size_t nloc = part[d + 1] - part[d];
+                VEXB_CHECKED(vexb_dspmat_create(queue[d].ordinal(), queue[d].raw(), d, plan, nloc, row + part[d], sizeof(idx_t),
+                                                col + row[part[d]], sizeof(col_t), val + row[part[d]], dtype_of<val_t>::value,
+                                                format, &mtx[d]));
+            }
+            if (nd > 1 && off[nd] > 0) comms = detail::communicators(queue);
+        }
+
+        SpMat(const SpMat&) = delete;
+        SpMat& operator=(const SpMat&) = delete;
+        SpMat(SpMat &&o) noexcept : SpMat() { swap(o); }
+        SpMat& operator=(SpMat &&o) noexcept { swap(o); return *this; }
+        ~SpMat() {
+            for (auto m : mtx) vexb_dspmat_destroy(m);
+            if (plan) vexb_halo_plan_destroy(plan);
+        }
+
+        /// y = alpha * A * x   or   y += alpha * A * x   (spmat.hpp:120-185).
+        void apply(const vex::vector<val_t> &x, vex::vector<val_t> &y, scalar_type alpha = 1, bool append = false) const {
+            precondition(x.size() == ncols && y.size() == nrows, "SpMat::apply: vector sizes do not match the matrix");
+            const int nd = static_cast<int>(queue.size());
+            std::vector<const void*> xs(nd); std::vector<void*> ys(nd), streams(nd);
+            for (int d = 0; d < nd; ++d) { xs[d] = x(d).raw(); ys[d] = y(d).raw(); streams[d] = queue[d].raw(); }
+            vexb_comm *const *cm = (comms && !comms->comms.empty()) ? comms->comms.data() : nullptr;
+            VEXB_CHECKED(vexb_dspmat_apply(nd, cm, mtx.data(), streams.data(), xs.data(), ys.data(), static_cast<double>(alpha), append));
+        }
+
+        size_t rows() const { return nrows; }
+        size_t cols() const { return ncols; }
+        size_t nonzeros() const { return nnz; }
+        vexb_dspmat_info info(unsigned d = 0) const { vexb_dspmat_info i; VEXB_CHECKED(vexb_dspmat_get_info(mtx[d], &i)); return i; }
+    private:
+        std::vector<backend::command_queue> queue;
+        std::vector<size_t> part, col_part;
+        size_t nrows, ncols, nnz;
+        vexb_halo_plan *plan;
+        std::vector<vexb_dspmat*> mtx;
+        std::shared_ptr<detail::comm_set> comms;
+
+        void swap(SpMat &o) {
+            std::swap(queue, o.queue); std::swap(part, o.part); std::swap(col_part, o.col_part);
+            std::swap(nrows, o.nrows); std::swap(ncols, o.ncols); std::swap(nnz, o.nnz);
+            std::swap(plan, o.plan); std::swap(mtx, o.mtx); std::swap(comms, o.comms);
+        }
+};
+
+template <typename val_t, typename col_t, typename idx_t>
+additive_operator<SpMat<val_t, col_t, idx_t>, vector<val_t>>
+operator*(const SpMat<val_t, col_t, idx_t> &A, const vector<val_t> &x) {
+    return additive_operator<SpMat<val_t, col_t, idx_t>, vector<val_t>>(A, x);
+}
+
+} // namespace vex
+#endif
