@@ -1,0 +1,95 @@
+"""Multi-GPU paths (skipped on a single-GPU box): NCCL halo exchange and all-reduce, one process
+driving several devices, and the one-process-per-GPU launch that bench.py uses."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+import vexcl_b200 as vx
+from vexcl_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def ndev():
+    n = C.c_int(0)
+    L.lib().vexb_device_count(C.byref(n))
+    return n.value
+
+
+@pytest.fixture(scope="module")
+def ctxn(built):
+    n = ndev()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    return vx.Context(list(range(min(n, 4))), use_nccl=True)
+
+
+def test_nccl_reduce_and_halo_single_process(ctxn):
+    nd = ctxn.nparts
+    n = 40000
+    X = oracle.uniform_real(3, n)
+    x = vx.vector(ctxn, X)
+    s = vx.Reductor(ctxn, np.float64, L.SUM)
+    ref = oracle.kahan_sum(X)
+    assert abs(s(x) - ref) <= 1e-10 * abs(ref)
+    assert vx.Reductor(ctxn, np.float64, L.MAX)(x) == X.max()
+    assert vx.Reductor(ctxn, np.float64, L.MIN)(x) == X.min()
+    assert vx.Reductor(ctxn, np.float64, L.MINMAX)(x) == (X.min(), X.max())
+    assert vx.Reductor(ctxn, np.int64, L.SUM)(x > 0.5) == int((X > 0.5).sum())
+    for dim, m in ((2, 200), (3, 34)):
+        row, col, val = oracle.poisson(dim, m)
+        N = row.size - 1
+        Xv = oracle.uniform_real(7, N)
+        part = oracle.partition(N, nd)
+        want = oracle.spmat_apply(part, part, row, col, val, Xv)
+        for fmt in (vx.FMT_CSR, vx.FMT_HELL):
+            A = vx.SpMat(ctxn, N, N, row, col, val, fmt)
+            xv, y = vx.vector(ctxn, Xv), vx.vector(ctxn, N)
+            for _ in range(3):                                   # repeated applies reuse the halo buffers
+                y.assign(A * xv)
+            mag = oracle.csr_absrow(row, col, val, Xv)
+            assert np.all(np.abs(y.read() - want) <= 1e-10 * mag)
+            y += 2 * (A * xv)
+            assert np.all(np.abs(y.read() - 3 * want) <= 3e-10 * mag)
+    row, col, val = oracle.random_matrix(5000, 5000, 12, seed=77)
+    Xv = oracle.uniform_real(8, 5000)
+    A = vx.SpMat(ctxn, 5000, 5000, row, col, val)
+    xv, y = vx.vector(ctxn, Xv), vx.vector(ctxn, 5000)
+    y.assign(A * xv)
+    want = oracle.csr_spmv(row, col, val, Xv)
+    assert np.all(np.abs(y.read() - want) <= 1e-10 * np.abs(want) + 1e-300)
+
+
+def test_copy_engine_halo_without_nccl(built):
+    if ndev() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ctx = vx.Context([0, 1], use_nccl=False)
+    row, col, val = oracle.poisson(2, 150)
+    N = row.size - 1
+    Xv = oracle.uniform_real(7, N)
+    A = vx.SpMat(ctx, N, N, row, col, val, vx.FMT_CSR)
+    xv, y = vx.vector(ctx, Xv), vx.vector(ctx, N)
+    y.assign(A * xv)
+    want = oracle.csr_spmv(row, col, val, Xv)
+    assert np.all(np.abs(y.read() - want) <= 1e-10 * oracle.csr_absrow(row, col, val, Xv))
+
+
+def test_bench_one_process_per_gpu(built):
+    n = ndev()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", str(ROOT / "bench.py"), "--gpus", "2", "--steps", "20", "--warmup", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["n_gpus"] == 2 and out["value"] > 0 and out["gpu_launches"] >= 20

@@ -138,7 +138,11 @@ extern "C" int vexb_dspmat_create(int dev, void *stream, int part, const vexb_ha
         if ((e = cudaMalloc(&A->ghost_buf, A->n_ghost * vs)) != cudaSuccess) return fail(e, "cudaMalloc");
         if ((e = cudaMemset(A->ghost_buf, 0, A->n_ghost * vs)) != cudaSuccess) return fail(e, "cudaMemset");
     }
-    if ((e = cudaStreamCreateWithFlags(&A->side, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    // The halo stream gets the highest priority so that its small transfer kernels are scheduled
+    // ahead of the thousands of CTAs of the local product they overlap with.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if ((e = cudaStreamCreateWithPriority(&A->side, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaEventCreateWithFlags(&A->ev_pack, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&A->ev_halo, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
     *out = A;
