@@ -19,13 +19,15 @@
 struct vexb_dspmat {
     int dev = 0, part = 0, nparts = 1, val_dtype = VEXB_F64;
     size_t nrows = 0, ncols_local = 0, n_ghost = 0, n_send = 0;
-    vexb_spmat *loc = nullptr, *rem = nullptr;
+    vexb_spmat *loc = nullptr;      // rows without ghost entries (all rows when there are no ghosts)
+    vexb_spmat *bnd = nullptr;      // local entries of the rows that also have ghost entries (row-compressed)
+    vexb_spmat *rem = nullptr;      // ghost entries of those rows (row-compressed)
     int *send_cols = nullptr;       // device: local x indices to pack, grouped by destination
     void *send_buf = nullptr;       // device: n_send values
     void *ghost_buf = nullptr;      // device: n_ghost values ("rx" of spmat.hpp:273)
     std::vector<size_t> send_counts, recv_counts;
     cudaStream_t side = nullptr;    // secondary queue (spmat.hpp:81-82)
-    cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_halo = nullptr, ev_x = nullptr;
     // host copies of the split, kept for parity checks
     std::vector<int64_t> loc_ptr, loc_col, rem_ptr, rem_col;
     std::vector<char> loc_val, rem_val;
@@ -51,11 +53,12 @@ using namespace vexb;
 extern "C" int vexb_dspmat_destroy(vexb_dspmat *A) {
     if (!A) return VEXB_OK;
     DeviceGuard g(A->dev);
-    vexb_spmat_destroy(A->loc); vexb_spmat_destroy(A->rem);
+    vexb_spmat_destroy(A->loc); vexb_spmat_destroy(A->bnd); vexb_spmat_destroy(A->rem);
     cudaFree(A->send_cols); cudaFree(A->send_buf); cudaFree(A->ghost_buf);
     if (A->side) cudaStreamDestroy(A->side);
     if (A->ev_pack) cudaEventDestroy(A->ev_pack);
     if (A->ev_halo) cudaEventDestroy(A->ev_halo);
+    if (A->ev_x) cudaEventDestroy(A->ev_x);
     delete A;
     return VEXB_OK;
 }
@@ -115,12 +118,44 @@ extern "C" int vexb_dspmat_create(int dev, void *stream, int part, const vexb_ha
         A->split_kept = true;
     }
 
-    int st = spmat_from_csr(dev, nrows, A->ncols_local, lrow, lcol, lval.data(), val_dtype, fmt, nullptr, &A->loc);
-    if (st == VEXB_OK && !rcol.empty()) {
-        // row-compress the remote strip
-        std::vector<int> ids, rrow(1, 0);
-        for (size_t i = 0; i < nrows; ++i) if (rrow_full[i + 1] > rrow_full[i]) { ids.push_back((int)i); rrow.push_back(rrow_full[i + 1]); }
-        st = spmat_from_csr(dev, nrows, A->n_ghost, rrow, rcol, rval.data(), val_dtype, fmt, &ids, &A->rem);
+    int st = VEXB_OK;
+    if (rcol.empty()) {
+        st = spmat_from_csr(dev, nrows, A->ncols_local, lrow, lcol, lval.data(), val_dtype, fmt, nullptr, &A->loc);
+    } else {
+        // Rows that own a ghost entry ("boundary" rows) are split off: the interior strip does not
+        // depend on the halo and runs on the main stream while the halo is in flight; the boundary rows
+        // (local entries, then ghost entries) follow the halo on the side stream.  Disjoint rows, no race on y.
+        // Interior = the longest run of consecutive rows without ghost entries (for slab partitions that is
+        // everything but a grid line or two at the ends): stored as a plain strip with a row offset, no row
+        // map.  If ghosts are scattered all over (longest run < 80 % of the rows) the interior is instead every
+        // ghost-free row, row-compressed.
+        size_t best_lo = 0, best_hi = 0, run_lo = 0;
+        for (size_t i = 0; i <= nrows; ++i) {
+            const bool boundary = i == nrows || rrow_full[i + 1] > rrow_full[i];
+            if (boundary) { if (i - run_lo > best_hi - best_lo) { best_lo = run_lo; best_hi = i; } run_lo = i + 1; }
+        }
+        const bool contiguous = (best_hi - best_lo) * 5 >= nrows * 4;
+        std::vector<int> bids, rids, irids, brow(1, 0), rrow(1, 0), irow(1, 0), bcol, icol;
+        std::vector<char> bval, ival;
+        for (size_t i = 0; i < nrows; ++i) {
+            const bool has_ghost = rrow_full[i + 1] > rrow_full[i];
+            const bool interior = contiguous ? (i >= best_lo && i < best_hi) : !has_ghost;
+            std::vector<int> &dc = interior ? icol : bcol;
+            std::vector<char> &dv = interior ? ival : bval;
+            dc.insert(dc.end(), lcol.begin() + lrow[i], lcol.begin() + lrow[i + 1]);
+            dv.insert(dv.end(), lval.begin() + (size_t)lrow[i] * vs, lval.begin() + (size_t)lrow[i + 1] * vs);
+            if (interior) { irids.push_back((int)i); irow.push_back((int)icol.size()); }
+            else { bids.push_back((int)i); brow.push_back((int)bcol.size()); }
+            if (has_ghost) { rids.push_back((int)i); rrow.push_back(rrow_full[i + 1]); }
+        }
+        if (contiguous) {
+            st = spmat_from_csr(dev, irids.size(), A->ncols_local, irow, icol, ival.data(), val_dtype, fmt, nullptr, &A->loc);
+            if (st == VEXB_OK) A->loc->y_offset = best_lo;
+        } else {
+            st = spmat_from_csr(dev, nrows, A->ncols_local, irow, icol, ival.data(), val_dtype, fmt, &irids, &A->loc);
+        }
+        if (st == VEXB_OK) st = spmat_from_csr(dev, nrows, A->ncols_local, brow, bcol, bval.data(), val_dtype, VEXB_FMT_CSR, &bids, &A->bnd);
+        if (st == VEXB_OK) st = spmat_from_csr(dev, nrows, A->n_ghost, rrow, rcol, rval.data(), val_dtype, VEXB_FMT_CSR, &rids, &A->rem);
     }
     if (st != VEXB_OK) { vexb_dspmat_destroy(A); return st; }
 
@@ -145,6 +180,7 @@ extern "C" int vexb_dspmat_create(int dev, void *stream, int part, const vexb_ha
     if ((e = cudaStreamCreateWithPriority(&A->side, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaEventCreateWithFlags(&A->ev_pack, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&A->ev_halo, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&A->ev_x, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
     *out = A;
     return VEXB_OK;
 }
@@ -189,7 +225,9 @@ extern "C" int vexb_dspmat_pack(const vexb_dspmat *A, void *stream, const void *
 
 extern "C" int vexb_dspmat_mul_local(const vexb_dspmat *A, void *stream, const void *x, void *y, double alpha, int append) {
     VEXB_CHECK(A && A->loc, "matrix is NULL");
-    return vexb_spmv(A->dev, stream, A->loc, x, y, alpha, append);
+    VEXB_TRY(vexb_spmv(A->dev, stream, A->loc, x, y, alpha, append));
+    if (A->bnd) VEXB_TRY(vexb_spmv(A->dev, stream, A->bnd, x, y, alpha, append));
+    return VEXB_OK;
 }
 
 extern "C" int vexb_dspmat_mul_remote(const vexb_dspmat *A, void *stream, void *y, double alpha) {
@@ -260,38 +298,38 @@ extern "C" int vexb_dspmat_apply(int nlocal, vexb_comm *const *comms, vexb_dspma
     VEXB_CHECK(nlocal >= 1 && parts && x && y, "bad arguments");
     bool halo = false;
     for (int k = 0; k < nlocal; ++k) { VEXB_CHECK(parts[k], "part %d is NULL", k); halo = halo || parts[k]->n_send || parts[k]->n_ghost; }
-    std::vector<void *> side(nlocal);
-    if (halo) {
-        // 1. gather the values the neighbours need (spmat.hpp:127-135); the side stream picks up after it
-        for (int k = 0; k < nlocal; ++k) {
-            const vexb_dspmat *A = parts[k];
-            cudaStream_t st = streams ? (cudaStream_t)streams[k] : nullptr;
-            if (!comms) {   // copy path: the previous apply's readers of my send buffer must be done
-                DeviceGuard g0(A->dev);
-                for (int d = 0; d < nlocal; ++d) if (d != k && A->send_counts[d]) VEXB_CUDA(cudaStreamWaitEvent(st, parts[d]->ev_halo, 0));
-            }
-            VEXB_TRY(vexb_dspmat_pack(A, st, x[k]));
-            DeviceGuard g(A->dev);
-            VEXB_CUDA(cudaEventRecord(A->ev_pack, st));
-            VEXB_CUDA(cudaStreamWaitEvent(A->side, A->ev_pack, 0));
-            side[k] = (void *)A->side;
-        }
+    if (!halo) {
+        for (int k = 0; k < nlocal; ++k)
+            VEXB_TRY(vexb_dspmat_mul_local(parts[k], streams ? streams[k] : nullptr, x[k], y[k], alpha, append));
+        return VEXB_OK;
     }
-    // 2. local product on the main stream (spmat.hpp:142-146) ...
+    std::vector<void *> side(nlocal);
+    // 1. side stream (high priority): wait for x, gather what the neighbours need (spmat.hpp:127-135)
+    for (int k = 0; k < nlocal; ++k) {
+        const vexb_dspmat *A = parts[k];
+        cudaStream_t st = streams ? (cudaStream_t)streams[k] : nullptr;
+        DeviceGuard g(A->dev);
+        VEXB_CUDA(cudaEventRecord(A->ev_x, st));
+        VEXB_CUDA(cudaStreamWaitEvent(A->side, A->ev_x, 0));
+        if (!comms)   // copy path: the previous apply's readers of my send buffer must be done
+            for (int d = 0; d < nlocal; ++d) if (d != k && A->send_counts[d]) VEXB_CUDA(cudaStreamWaitEvent(A->side, parts[d]->ev_halo, 0));
+        VEXB_TRY(vexb_dspmat_pack(A, A->side, x[k]));
+        VEXB_CUDA(cudaEventRecord(A->ev_pack, A->side));
+        side[k] = (void *)A->side;
+    }
+    // 2. main stream: rows that need no ghosts (spmat.hpp:142-146), concurrently with ...
     for (int k = 0; k < nlocal; ++k)
-        VEXB_TRY(vexb_dspmat_mul_local(parts[k], streams ? streams[k] : nullptr, x[k], y[k], alpha, append));
-    if (halo) {
-        // 3. ... while the halo moves over NVLink on the side streams (replaces spmat.hpp:149-176)
-        VEXB_TRY(vexb_halo_exchange(nlocal, comms, parts, side.data()));
-        // 4. remote product once the ghosts have landed (spmat.hpp:178-183)
-        for (int k = 0; k < nlocal; ++k) {
-            const vexb_dspmat *A = parts[k];
-            cudaStream_t st = streams ? (cudaStream_t)streams[k] : nullptr;
-            DeviceGuard g(A->dev);
-            VEXB_CUDA(cudaEventRecord(A->ev_halo, A->side));
-            VEXB_CUDA(cudaStreamWaitEvent(st, A->ev_halo, 0));
-            VEXB_TRY(vexb_dspmat_mul_remote(A, st, y[k], alpha));
-        }
+        VEXB_TRY(vexb_spmv(parts[k]->dev, streams ? streams[k] : nullptr, parts[k]->loc, x[k], y[k], alpha, append));
+    // 3. ... the halo over NVLink on the side streams (replaces spmat.hpp:149-176), then the boundary rows
+    if (!param("dspmat.debug_skip_exchange", 0)) VEXB_TRY(vexb_halo_exchange(nlocal, comms, parts, side.data()));
+    for (int k = 0; k < nlocal; ++k) {
+        const vexb_dspmat *A = parts[k];
+        cudaStream_t st = streams ? (cudaStream_t)streams[k] : nullptr;
+        if (A->bnd) VEXB_TRY(vexb_spmv(A->dev, A->side, A->bnd, x[k], y[k], alpha, append));
+        VEXB_TRY(vexb_dspmat_mul_remote(A, A->side, y[k], alpha));                 // spmat.hpp:178-183
+        DeviceGuard g(A->dev);
+        VEXB_CUDA(cudaEventRecord(A->ev_halo, A->side));
+        VEXB_CUDA(cudaStreamWaitEvent(st, A->ev_halo, 0));
     }
     return VEXB_OK;
 }

@@ -16,6 +16,7 @@ struct vexb_spmat {
     int *ell_col = nullptr; void *ell_val = nullptr;
     int *tail_ptr = nullptr; int *tail_col = nullptr; void *tail_val = nullptr;
     int *row_ids = nullptr;        // optional: compressed rows, y index of stored row r (remote strips)
+    size_t y_offset = 0;           // y index of stored row 0 when the strip covers a contiguous row range
     size_t nrows_stored = 0;       // rows held in the arrays (== nrows unless row_ids)
     size_t device_bytes = 0;
 };

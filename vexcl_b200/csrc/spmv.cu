@@ -342,9 +342,9 @@ __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w
 }
 
 template <class T>
-__global__ void zero_or_keep_kernel(T *y, size_t n) {
+__global__ void zero_rows_kernel(T *y, size_t n, const int *__restrict__ row_ids) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = T(0);
+    if (i < n) y[row_ids ? (size_t)row_ids[i] : i] = T(0);
 }
 
 template <class T>
@@ -435,14 +435,16 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
 
 template <class T>
 static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T alpha, int append) {
-    if (A->nrows == 0) return VEXB_OK;
-    if (A->row_ids && !append) VEXB_FAIL(VEXB_ERR_INVALID, "row-compressed strips only support y += alpha*A*x");
+    // A strip touches exactly its stored rows: all of y[0, nrows) normally, y[row_ids[r]] for a
+    // row-compressed strip, y[y_offset + r] for a strip that covers a contiguous sub-range.
+    const size_t n = A->nrows_stored;
+    if (n == 0) return VEXB_OK;
+    y += A->y_offset;
     if (A->nnz == 0) {
         // y = A*x with an empty strip must still zero y (csr.inl:195-200)
-        if (!append) { zero_or_keep_kernel<T><<<(unsigned)((A->nrows + 255) / 256), 256, 0, st>>>(y, A->nrows); VEXB_LAUNCHED(); }
+        if (!append) { zero_rows_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, n, A->row_ids); VEXB_LAUNCHED(); }
         return VEXB_OK;
     }
-    const size_t n = A->nrows_stored;
     if (A->fmt == VEXB_FMT_CSR && param("spmv.pipeline", 0)) {
         long stages = param("spmv.stages", 4);
         stages = std::max(2l, std::min(stages, 16l));
