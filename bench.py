@@ -348,6 +348,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             got = y.read()
             err = float(np.max(np.abs(got - y_cpu) / (np.abs(y_cpu) + 1e-300)))
             extra["parity_max_rel_err_vs_oracle"] = err
+    if not args.no_cg:
+        # configs[4]: one CG iteration (SpMV + 2 axpy + 2 dot + p update) on the 3-D 7-pt Poisson matrix
+        del A, x, y
+        try:
+            extra["cg_step"] = bench_cg(ctx, vx, rank, world, args, barrier, max_over_ranks, peak)
+        except vx.VexbError as e:
+            extra["cg_step"] = {"error": str(e)}
 
     if rank == 0:
         line = {
@@ -370,6 +377,49 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if dist is not None:
         barrier()
         dist.destroy_process_group()
+
+
+def bench_cg(ctx, vx, rank, world, args, barrier, max_over_ranks, peak):
+    """configs[4]: CG iteration on the 3-D 7-point Poisson matrix (examples/benchmark.cpp:357-415 generator).
+    Grid: 512^3 when 8 ranks (the named configuration: 16.7M rows per GPU), else 256 x 256 x (256 * ranks)
+    (the same slab per GPU).  Device-resident alpha / beta, one CUDA graph per iteration."""
+    from vexcl_b200 import gen
+    from vexcl_b200.solvers import CGDevice, cg_bytes_per_iteration
+    if world == 8:
+        nx = ny = nz = 512
+    else:
+        nx = ny = 256
+        nz = 256 * world
+    N = nx * ny * nz
+    k = ctx.local[0]
+    part = ctx.partition(N)
+    r0, r1 = int(part[k]), int(part[k + 1])
+    row, col, val = gen.poisson_strip(3, nx, ny, nz, r0=r0, r1=r1)
+    val /= float((nx - 1) ** 2)                                   # O(1) entries so that the iteration stays finite
+    A = vx.SpMat(ctx, N, N, row, col, val, vx.FMT_AUTO, strip=True)
+    _, nnz_total = gen.poisson_nnz(3, nx, ny, nz)
+    del row, col, val
+    b, x = vx.vector(ctx, N), vx.vector(ctx, N)
+    b.assign(vx.ElementIndex() * (1.0 / N) + 0.5)
+    x.assign(0.0)
+    cg = CGDevice(A, b, x)
+    iters = max(10, min(args.steps, 50))
+    out = {}
+    for mode in ("stream", "graph"):
+        if mode == "graph":
+            try:
+                cg.capture()
+            except vx.VexbError as e:
+                out["graph_error"] = str(e)
+                break
+        ms = max_over_ranks(time_loop(ctx, lambda: cg.run(1), iters, 3, barrier))
+        nbytes = cg_bytes_per_iteration(N, gen.spmv_bytes(N, N, nnz_total))
+        gbs = nbytes * iters / (ms * 1e-3) / 1e9
+        out[mode] = {"ms_per_iteration": ms / iters, "gbs": gbs, "frac_of_aggregate_hbm_peak": gbs / (peak * world)}
+    out.update({"grid": [nx, ny, nz], "rows": N, "nnz": nnz_total, "bytes_per_iteration": nbytes,
+                "convention": "unfused reference-equivalent traffic: SpMV + dot 16N + axpy 24N + axpy 24N + dot 8N + p-update 24N",
+                "residual2_after": cg.residual2()})
+    return out
 
 
 def bench_vectors(ctx, vx, args, peak):
@@ -404,6 +454,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cg", action="store_true")
     ap.add_argument("--format", default="auto", choices=["auto", "csr", "hell"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

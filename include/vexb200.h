@@ -89,7 +89,9 @@ typedef enum {
 typedef enum {
     VEXB_TERM_VEC = 0,    /* v.ptr: device array of `dtype`, element i of this device slice */
     VEXB_TERM_SCALAR = 1, /* by-value scalar of `dtype` (operations.hpp:168-175)            */
-    VEXB_TERM_INDEX = 2   /* element_index: index_offset + i + v.i64 (element_index.hpp:40-111), type u64 */
+    VEXB_TERM_INDEX = 2,  /* element_index: index_offset + i + v.i64 (element_index.hpp:40-111), type u64 */
+    VEXB_TERM_DSCALAR = 3 /* v.ptr: ONE device-resident value of `dtype`, broadcast to every element.  Lets the
+                             result of vexb_reduce feed the next expression without a host round trip. */
 } vexb_term_kind;
 
 typedef struct {
@@ -247,6 +249,20 @@ int vexb_comm_rank(const vexb_comm *comm, int *rank, int *nranks, int *dev);
 int vexb_comm_allreduce(int nlocal, vexb_comm *const *comms, void *const *bufs, void *const *streams,
                         int count, int dtype, int op);
 int vexb_comm_barrier(int nlocal, vexb_comm *const *comms, void *const *streams);
+
+/* ------------------------------------------------------------------------
+ * CUDA graphs: record everything enqueued on `stream` (and on streams that
+ * fork from / join it through events, e.g. the halo side stream and its NCCL
+ * calls) between begin and end, then replay it with one launch.  Replaces the
+ * per-kernel host launch loop of the reference for launch-bound inner loops
+ * (a CG iteration at 8 GPUs).  Only asynchronous entry points may be called
+ * while capturing (no blocking copies, no vexb_reduce_fetch).
+ * ---------------------------------------------------------------------- */
+typedef struct vexb_graph vexb_graph;
+int vexb_graph_begin(int dev, void *stream);
+int vexb_graph_end(int dev, void *stream, vexb_graph **graph);
+int vexb_graph_launch(vexb_graph *graph, void *stream);
+int vexb_graph_destroy(vexb_graph *graph);
 
 /* ------------------------------------------------------------------------
  * Halo plan (host only; no GPU needed): who sends which x entries to whom.

@@ -307,3 +307,24 @@ def spmat_apply(part, col_part, row, col, val, x, y=None, alpha=1.0, append=Fals
             ys = csr_spmv(rr, rc, rv, rx[ex["cols_to_recv"][d]], ys, alpha, True)
         y[part[d]:part[d + 1]] = ys
     return y
+
+
+# ---------------------------------------------------------------------------- CG (composition check)
+def cg(row, col, val, b, x0, iters):
+    """Conjugate gradient from the oracle's own pieces, the way vexcl/external/viennacl.hpp:36-64 lets
+    ViennaCL compose it: prod -> csr_spmv, inner_prod -> reduce_dot, vector updates in plain numpy."""
+    x = _f64(x0).copy()
+    r = _f64(b) - csr_spmv(row, col, val, x)
+    p = r.copy()
+    rho = reduce_dot(r, r, kahan=True)
+    hist = []
+    for _ in range(iters):
+        q = csr_spmv(row, col, val, p)
+        alpha = rho / reduce_dot(p, q, kahan=True)
+        x = x + alpha * p
+        r = r - alpha * q
+        rho_new = reduce_dot(r, r, kahan=True)
+        p = r + (rho_new / rho) * p
+        rho = rho_new
+        hist.append(rho)
+    return x, hist

@@ -1,0 +1,70 @@
+"""CG step (BASELINE configs[4]: SpMV + 2 axpy + 2 dot) built from the three hot paths; checked against the
+oracle's composition on a small 3-D Poisson problem.  Covers device-resident scalars and CUDA-graph replay."""
+import numpy as np
+import pytest
+
+import oracle
+import vexcl_b200 as vx
+from vexcl_b200 import _lib as L
+from vexcl_b200.api import DeviceScalar
+from vexcl_b200.solvers import CGDevice, cg_host_scalars
+
+pytestmark = pytest.mark.gpu
+
+
+def problem(n=20):
+    row, col, val = oracle.poisson(3, n)
+    N = row.size - 1
+    val = val / float((n - 1) ** 2)                      # scale to O(1) entries
+    b = oracle.uniform_real(3, N)
+    return row, col, val, b, N
+
+
+def test_device_scalars_in_expressions(ctx1):
+    n = 10001
+    X = oracle.uniform_real(1, n)
+    x, y = vx.vector(ctx1, X), vx.vector(ctx1, n)
+    s, t = DeviceScalar(ctx1, value=2.5), DeviceScalar(ctx1)
+    vx.Reductor(ctx1, np.float64, L.SUM).device(x * x, t)
+    assert abs(t.get() - np.dot(X, X)) <= 1e-10 * np.dot(X, X)
+    z = vx.vector(ctx1, X[::-1].copy())
+    y.assign(s * x + z)                                   # sweep kernel with a device-resident coefficient
+    assert y.eval_path(L.SET, s * x + z) == "sweep:axpy"
+    assert np.array_equal(y.read(), 2.5 * X + X[::-1])
+    t.assign(s / 4.0 + 1.0)
+    assert t.get() == 2.5 / 4.0 + 1.0
+    y.assign(vx.sin(x) * t)                               # interpreter path
+    assert np.allclose(y.read(), np.sin(X) * t.get(), rtol=1e-15)
+
+
+@pytest.mark.parametrize("fmt", [L.FMT_CSR, L.FMT_HELL])
+def test_cg_matches_oracle(ctx, fmt):
+    row, col, val, b, N = problem()
+    iters = 25
+    xo, hist_o = oracle.cg(row, col, val, b, np.zeros(N), iters)
+    A = vx.SpMat(ctx, N, N, row, col, val, fmt)
+    bv, x = vx.vector(ctx, b), vx.vector(ctx, N)
+    x.assign(0.0)
+    hist = cg_host_scalars(A, bv, x, iters)
+    assert hist[-1] < 1e-3 * hist[0]
+    assert np.allclose(hist, hist_o, rtol=1e-8)
+    assert np.allclose(x.read(), xo, rtol=1e-8, atol=1e-12)
+
+
+def test_cg_device_scalars_and_graph(ctx1):
+    row, col, val, b, N = problem()
+    iters = 25
+    xo, hist_o = oracle.cg(row, col, val, b, np.zeros(N), iters)
+    A = vx.SpMat(ctx1, N, N, row, col, val)
+    for use_graph in (False, True):
+        bv, x = vx.vector(ctx1, b), vx.vector(ctx1, N)
+        x.assign(0.0)
+        cg = CGDevice(A, bv, x)
+        if use_graph:
+            cg.capture()                                   # performs iteration 1 while warming up
+            cg.run(iters - 1)
+        else:
+            cg.run(iters)
+        ctx1.finish()
+        assert abs(cg.residual2() - hist_o[-1]) <= 1e-8 * hist_o[-1]
+        assert np.allclose(x.read(), xo, rtol=1e-8, atol=1e-12)

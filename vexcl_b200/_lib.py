@@ -15,7 +15,7 @@ OK = 0
 F64, F32, I32, U32, I64, U64 = range(6)
 SET, ADD, SUB, MUL, DIV, MOD, AND, OR, XOR, LSH, RSH = range(11)
 SUM, SUM_KAHAN, MAX, MIN, MINMAX = range(5)
-TERM_VEC, TERM_SCALAR, TERM_INDEX = range(3)
+TERM_VEC, TERM_SCALAR, TERM_INDEX, TERM_DSCALAR = range(4)
 FMT_AUTO, FMT_CSR, FMT_HELL = range(3)
 MAX_TERMS, MAX_CODE, MAX_STACK = 16, 64, 12
 
@@ -119,6 +119,8 @@ def lib():
         "vexb_comm_rank": ([vp, P(i), P(i), P(i)], i),
         "vexb_comm_allreduce": ([i, P(vp), P(vp), P(vp), i, i, i], i),
         "vexb_comm_barrier": ([i, P(vp), P(vp)], i),
+        "vexb_graph_begin": ([i, vp], i), "vexb_graph_end": ([i, vp, P(vp)], i),
+        "vexb_graph_launch": ([vp, vp], i), "vexb_graph_destroy": ([vp], i),
         "vexb_strip_ghost_cols": ([sz, vp, i, vp, i, sz, sz, vp, P(sz)], i),
         "vexb_halo_plan_create": ([i, P(sz), vp, P(sz), P(vp)], i),
         "vexb_halo_plan_destroy": ([vp], i),

@@ -163,6 +163,7 @@ class Context:
 class Node:
     """Expression tree node (the analogue of a Boost.Proto expression, operations.hpp:455-512)."""
     dtype: int = L.F64
+    __array_ufunc__ = None          # numpy scalars defer to our reflected operators (np.float64(2) * v)
 
     def _bin(self, op, other, swap=False):
         o = wrap(other)
@@ -358,6 +359,7 @@ def _find_props(n: Node):
 # ------------------------------------------------------------------------------------------- SpMV additive terms
 class SpMVTerm:
     """`A * x`, possibly scaled: the additive_operator of operations.hpp:759-776."""
+    __array_ufunc__ = None
     def __init__(self, A, x, scale=1.0):
         self.A, self.x, self.scale = A, x, scale
 
@@ -373,6 +375,7 @@ class SpMVTerm:
 
 class Mixed:
     """vector expression + additive terms, split as vector.hpp:758-763 / operations.hpp:1463-1576."""
+    __array_ufunc__ = None
     def __init__(self, vec: Optional[Node], terms):
         self.vec, self.terms = vec, list(terms)
 
@@ -738,3 +741,119 @@ class Event:
         ms = C.c_float()
         L.check(L.lib().vexb_event_elapsed_ms(self.h, later.h, C.byref(ms)))
         return ms.value
+
+
+# ------------------------------------------------------------------------------------------- device-resident scalars, graphs
+class DeviceScalar(Node):
+    """One value per device slot, kept in device memory (VEXB_TERM_DSCALAR).  A Reductor can leave its
+    result here (`Reductor.device`), scalar arithmetic on it is an n = 1 elementwise evaluation, and any
+    vector expression can use it as a coefficient -- so an iteration such as CG needs no host round trip
+    for alpha / beta and can be captured in a CUDA graph."""
+
+    def __init__(self, ctx: Context, dtype=np.float64, value=0):
+        lib = L.lib()
+        self.ctx, self.np_dtype, self.dtype = ctx, np.dtype(dtype), _vdt(dtype)
+        self.bufs = {}
+        for k in ctx.local:
+            p = C.c_void_p()
+            L.check(lib.vexb_malloc(ctx.devs[k], 64, C.byref(p)))
+            self.bufs[k] = p
+        self.set(value)
+
+    def __del__(self):
+        try:
+            for k, p in self.bufs.items():
+                L.lib().vexb_free(self.ctx.devs[k], p)
+        except Exception:
+            pass
+
+    def set(self, value):
+        h = np.full(2, value, dtype=self.np_dtype)
+        for k in self.ctx.local:
+            L.check(L.lib().vexb_h2d(self.ctx.devs[k], self.bufs[k], h.ctypes.data, 2 * self.np_dtype.itemsize, self.ctx.streams[k], 1))
+
+    def get(self):
+        k = self.ctx.local[0]
+        h = np.empty(1, dtype=self.np_dtype)
+        L.check(L.lib().vexb_d2h(self.ctx.devs[k], h.ctypes.data, self.bufs[k], self.np_dtype.itemsize, self.ctx.streams[k], 1))
+        return h[0]
+
+    def assign(self, rhs):
+        """self = scalar expression of DeviceScalars / constants (asynchronous, n = 1 on every slot)."""
+        rhs = wrap(rhs)
+        for k in self.ctx.local:
+            low = _Lowering(k, 0)
+            low.size = 1
+            low.lower(rhs)
+            L.check(L.lib().vexb_eval(self.ctx.devs[k], self.ctx.streams[k], self.bufs[k], self.dtype, L.SET, C.byref(low.e), 1, 0))
+        return self
+
+
+_lower_base = _Lowering.lower
+
+
+def _lower_with_dscalar(self, n):
+    if isinstance(n, DeviceScalar):
+        self.emit("TERM", n.dtype, self.term(L.TERM_DSCALAR, n.dtype, ptr=n.bufs[self.part].value))
+    else:
+        _lower_base(self, n)
+
+
+_Lowering.lower = _lower_with_dscalar
+
+
+def _reduce_device(self, expr, out: DeviceScalar):
+    """Reduce `expr` and leave the (all-reduced) result in `out` on every device; asynchronous."""
+    lib = L.lib()
+    ctx = self.ctx
+    expr = wrap(expr)
+    props = _find_props(expr)
+    if props is None:
+        raise ValueError("expression has no vector terminal")
+    if self.kind == L.MINMAX:
+        raise ValueError("MIN_MAX needs two result slots; use the host-returning call")
+    part = ctx.partition(props[1])
+    for k in ctx.local:
+        ws, _ = ctx.workspace(k)
+        low = _Lowering(k, int(part[k]))
+        low.lower(expr)
+        L.check(lib.vexb_reduce(ctx.devs[k], ctx.streams[k], C.byref(low.e), self.dtype, int(part[k + 1] - part[k]),
+                                int(part[k]), self.kind, out.bufs[k], ws))
+    if ctx.nparts > 1:
+        if ctx.comms is None:
+            raise RuntimeError("device-resident reductions over several slots need a communicator (NCCL)")
+        L.check(lib.vexb_comm_allreduce(len(ctx.local), ctx._arr(ctx.comms), ctx._arr(out.bufs), ctx._arr(ctx.streams),
+                                        1, self.dtype, self.kind))
+    return out
+
+
+Reductor.device = _reduce_device
+
+
+class Graph:
+    """Capture the asynchronous work issued by `fn()` on every local slot into CUDA graphs; replay with launch()."""
+
+    def __init__(self, ctx: Context, fn):
+        lib = L.lib()
+        self.ctx = ctx
+        for k in ctx.local:
+            L.check(lib.vexb_graph_begin(ctx.devs[k], ctx.streams[k]))
+        try:
+            fn()
+        finally:
+            self.h = {}
+            for k in ctx.local:
+                g = C.c_void_p()
+                L.check(lib.vexb_graph_end(ctx.devs[k], ctx.streams[k], C.byref(g)))
+                self.h[k] = g
+
+    def launch(self):
+        for k in self.ctx.local:
+            L.check(L.lib().vexb_graph_launch(self.h[k], self.ctx.streams[k]))
+
+    def __del__(self):
+        try:
+            for g in self.h.values():
+                L.lib().vexb_graph_destroy(g)
+        except Exception:
+            pass

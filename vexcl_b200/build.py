@@ -48,7 +48,9 @@ def _run(cmd, **kw):
 
 def build_lib(force: bool = False, verbose_ptxas: bool = False) -> Path:
     cus = sorted(CSRC.glob("*.cu"))
-    deps = list(CSRC.glob("*")) + [ROOT / "include" / "vexb200.h"]
+    deps = [p for p in CSRC.glob("*") if p.is_file()] + [ROOT / "include" / "vexb200.h"]
+    if not force and not _stale(LIB, deps):
+        return LIB          # e.g. on the GPU box: the .so travels with the repo, the object files do not
     objdir = CSRC / "obj"
     objdir.mkdir(exist_ok=True)
     objs = []

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) sweep_kernel(T *lhs, SweepArgs a, size_t 
     typedef Lanes<T> L;
     constexpr int E = L::E;
     constexpr int K = S::K;
-    const T sc[2] = {(T)a.s[0], (T)a.s[1]};
+    const T sc[2] = {sweep_scalar<T>(a, 0), sweep_scalar<T>(a, 1)};
     const size_t nvec = n / E;
     const size_t stride = (size_t)gridDim.x * blockDim.x * U;
     for (size_t base = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < nvec; base += stride) {
@@ -133,7 +133,9 @@ static bool plan_sweep(const void *lhs, int lhs_dtype, int aop, const vexb_expr 
         if (!aligned32(a.v[j])) return false;
     }
     for (int j = 0; j < 2; ++j) if (m.sslot[j] >= 0) {
-        if (!scalar_as_double(e.term[m.sslot[j]], &a.s[j])) return false;
+        const vexb_term &t = e.term[m.sslot[j]];
+        if (t.kind == VEXB_TERM_DSCALAR) a.sp[j] = t.v.ptr;          // dtype == lhs dtype (checked by the signature)
+        else if (!scalar_as_double(t, &a.s[j])) return false;
     }
     *mm = m; *args = a;
     return true;

@@ -54,6 +54,15 @@ __device__ __forceinline__ V load_term(const vexb_term &t, size_t idx, size_t in
             case VEXB_I64: r.i = t.v.i64; break;
             default:       r.u = t.v.u64; break;
         }
+    } else if (t.kind == VEXB_TERM_DSCALAR) {   // one device-resident value, same for every element
+        switch (t.dtype) {
+            case VEXB_F64: r.f = *(const double *)t.v.ptr; break;
+            case VEXB_F32: r.f = (double)*(const float *)t.v.ptr; break;
+            case VEXB_I32: r.i = (long long)*(const int *)t.v.ptr; break;
+            case VEXB_U32: r.u = (unsigned long long)*(const unsigned *)t.v.ptr; break;
+            case VEXB_I64: r.i = *(const long long *)t.v.ptr; break;
+            default:       r.u = *(const unsigned long long *)t.v.ptr; break;
+        }
     } else { // VEXB_TERM_INDEX
         r.u = (unsigned long long)(index_offset + idx) + (unsigned long long)t.v.i64;
     }

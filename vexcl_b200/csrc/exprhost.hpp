@@ -85,9 +85,9 @@ inline int normalize_expr(const vexb_expr *in, vexb_expr *out, bool need_ptrs = 
     VEXB_CHECK(in->n_code >= 1 && in->n_code <= VEXB_MAX_CODE, "n_code=%d out of range", in->n_code);
     for (int k = 0; k < in->n_terms; ++k) {
         const vexb_term &t = in->term[k];
-        VEXB_CHECK(t.kind <= VEXB_TERM_INDEX, "term %d: bad kind %d", k, (int)t.kind);
+        VEXB_CHECK(t.kind <= VEXB_TERM_DSCALAR, "term %d: bad kind %d", k, (int)t.kind);
         VEXB_CHECK(t.dtype <= VEXB_U64, "term %d: bad dtype %d", k, (int)t.dtype);
-        VEXB_CHECK(!need_ptrs || t.kind != VEXB_TERM_VEC || t.v.ptr != nullptr, "term %d: NULL device pointer", k);
+        VEXB_CHECK(!need_ptrs || (t.kind != VEXB_TERM_VEC && t.kind != VEXB_TERM_DSCALAR) || t.v.ptr != nullptr, "term %d: NULL device pointer", k);
     }
     // 1. de-duplicate vector terminals (same pointer, same dtype) and drop unused ones.
     int remap[VEXB_MAX_TERMS];
@@ -104,9 +104,9 @@ inline int normalize_expr(const vexb_expr *in, vexb_expr *out, bool need_ptrs = 
             VEXB_CHECK(ins.arg < in->n_terms, "instr %d: term slot %d out of range", pc, (int)ins.arg);
             const vexb_term &t = in->term[ins.arg];
             int slot = remap[ins.arg];
-            if (slot < 0 && t.kind == VEXB_TERM_VEC) {
+            if (slot < 0 && (t.kind == VEXB_TERM_VEC || t.kind == VEXB_TERM_DSCALAR)) {
                 for (int j = 0; j < out->n_terms; ++j)
-                    if (out->term[j].kind == VEXB_TERM_VEC && out->term[j].v.ptr == t.v.ptr && out->term[j].dtype == t.dtype) { slot = j; break; }
+                    if (out->term[j].kind == t.kind && out->term[j].v.ptr == t.v.ptr && out->term[j].dtype == t.dtype) { slot = j; break; }
             }
             if (slot < 0) { slot = out->n_terms++; out->term[slot] = t; memset(out->term[slot].pad, 0, sizeof(t.pad)); }
             remap[ins.arg] = slot;
@@ -187,7 +187,7 @@ inline std::string expr_signature(const vexb_expr &e, int T, int (&vs)[VEXB_MAX_
             if (t.kind == VEXB_TERM_VEC) {
                 if (vnum[in.arg] < 0) { vnum[in.arg] = nv; vs[nv++] = in.arg; }
                 sig += "V"; sig += char('0' + vnum[in.arg]);
-            } else if (t.kind == VEXB_TERM_SCALAR) {
+            } else if (t.kind == VEXB_TERM_SCALAR || t.kind == VEXB_TERM_DSCALAR) {
                 if (snum[in.arg] < 0) { snum[in.arg] = ns; ss[ns++] = in.arg; }
                 sig += "S"; sig += char('0' + snum[in.arg]);
             } else return "";

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) reduce_sweep_kernel(SweepArgs a, size_t n
     typedef Lanes<T> L;
     constexpr int E = L::E;
     constexpr int K = S::K;
-    const T sc[2] = {(T)a.s[0], (T)a.s[1]};
+    const T sc[2] = {sweep_scalar<T>(a, 0), sweep_scalar<T>(a, 1)};
     Fold<OP, T> acc[U][E];
 #pragma unroll
     for (int u = 0; u < U; ++u)

@@ -45,7 +45,13 @@ VEXB_SHAPE(SH_ABSDIFF, 2, A::abs(A::sub(v[0], v[1])))
 struct SweepArgs {
     const void *v[3];
     double s[2];
+    const void *sp[2];      // non-NULL: the scalar lives in device memory (VEXB_TERM_DSCALAR), of the kernel's type T
 };
+
+template <class T>
+__device__ __forceinline__ T sweep_scalar(const SweepArgs &a, int k) {
+    return a.sp[k] ? *static_cast<const T *>(a.sp[k]) : static_cast<T>(a.s[k]);
+}
 
 // 32 bytes = 4 doubles or 8 floats, moved with one 256-bit instruction.
 struct alignas(32) Vec256 { unsigned long long w[4]; };
