@@ -14,8 +14,12 @@
 #include "tagged_terminal.hpp"
 #include "reductor.hpp"
 #include "spmat.hpp"
+#include "sparse/product.hpp"
+#include "sparse/matrix.hpp"
+#include "sparse/distributed.hpp"
 
 namespace vex {
+using backend::command_queue;
 // Run-time compile option / header stacks and kernel caches have no meaning without run-time
 // compilation; kept as no-ops so existing programs build (cache.hpp:170-183, backend/common.hpp:111-206).
 inline void purge_caches() {}

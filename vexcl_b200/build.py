@@ -86,7 +86,7 @@ def build_cpp_tests(force: bool = False):
     if not src_dir.exists():
         return outs
     headers = list((ROOT / "include").rglob("*.h*")) + list(src_dir.glob("*.hpp"))
-    for cpp in sorted(src_dir.glob("*.cpp")):
+    for cpp in sorted(src_dir.glob("*.cpp")) + sorted((ROOT / "examples").glob("*.cpp")):
         bin_dir.mkdir(exist_ok=True)
         out = bin_dir / cpp.stem
         outs.append(out)

@@ -215,11 +215,11 @@ extern "C" int vexb_eval(int dev, void *stream, void *lhs, int lhs_dtype, int as
     vexb_expr prog;
     if (assign_op != VEXB_SET) { VEXB_TRY(fold_compound(e, lhs, lhs_dtype, assign_op, &prog)); }
     else prog = e;
-    const size_t per_block = 256 * 2;
+    const size_t per_block = 256 * 4;
     size_t want = (n + per_block - 1) / per_block;
-    const size_t cap = (size_t)sms * (size_t)param("interp.blocks_per_sm", 6);
+    const size_t cap = (size_t)sms * (size_t)param("interp.blocks_per_sm", 4);
     const int blocks = (int)(want < cap ? want : cap);
-    interp_kernel<2><<<blocks, 256, 0, st>>>(prog, lhs, lhs_dtype, n, index_offset);
+    interp_kernel<4><<<blocks, 256, 0, st>>>(prog, lhs, lhs_dtype, n, index_offset);
     VEXB_LAUNCHED();
     return VEXB_OK;
 }

@@ -244,39 +244,62 @@ __device__ __forceinline__ void eval_expr(const vexb_expr &e, const size_t (&idx
 #pragma unroll
     for (int k = 0; k < U; ++k) tos[k].u = 0;
     const int n_code = e.n_code;
+    // The dispatch is outside the lane loops, and double-precision arithmetic on double vectors -- the
+    // common case -- has its own arms, so the cost of decoding an instruction is shared by U elements.
+#define VEXB_LANES _Pragma("unroll") for (int k = 0; k < U; ++k)
     for (int pc = 0; pc < n_code; ++pc) {
         const vexb_instr in = e.code[pc];
         const int op = in.op, t = in.type;
-        if (op == VEXB_OP_TERM) {
-            if (d > 0) {
-#pragma unroll
-                for (int k = 0; k < U; ++k) st[d - 1][k] = tos[k];
+        switch (op) {
+            case VEXB_OP_TERM: {
+                if (d > 0) { VEXB_LANES st[d - 1][k] = tos[k]; }
+                const vexb_term &tm = e.term[in.arg];
+                if (tm.kind == VEXB_TERM_VEC && tm.dtype == VEXB_F64) {
+                    const double *p = (const double *)tm.v.ptr;
+                    VEXB_LANES tos[k].f = active[k] ? __ldcs(p + idx[k]) : 0.0;
+                } else {
+                    VEXB_LANES tos[k] = load_term(tm, idx[k], index_offset, active[k]);
+                }
+                ++d;
+                break;
             }
-            const vexb_term &tm = e.term[in.arg];
-#pragma unroll
-            for (int k = 0; k < U; ++k) tos[k] = load_term(tm, idx[k], index_offset, active[k]);
-            ++d;
-        } else if (op == VEXB_OP_CVT) {
-#pragma unroll
-            for (int k = 0; k < U; ++k) tos[k] = convert(tos[k], in.arg, t);
-        } else if (op == VEXB_OP_SELECT || op == VEXB_OP_FMA) {
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-                const V a = st[d - 3][k], b = st[d - 2][k], c = tos[k];
-                if (op == VEXB_OP_SELECT) tos[k] = (a.i != 0) ? b : c;
-                else if (t == VEXB_F32) tos[k].f = (double)__fmaf_rn((float)a.f, (float)b.f, (float)c.f);
-                else tos[k].f = __fma_rn(a.f, b.f, c.f);
-            }
-            d -= 2;
-        } else if ((op >= VEXB_OP_ADD && op <= VEXB_OP_LOR) || (op >= VEXB_OP_POW && op <= VEXB_OP_FMAX)) {
-#pragma unroll
-            for (int k = 0; k < U; ++k) tos[k] = binary_op(op, t, st[d - 2][k], tos[k]);
-            --d;
-        } else {
-#pragma unroll
-            for (int k = 0; k < U; ++k) tos[k] = unary_op(op, t, tos[k]);
+            case VEXB_OP_CVT:
+                VEXB_LANES tos[k] = convert(tos[k], in.arg, t);
+                break;
+            case VEXB_OP_ADD:
+                if (t == VEXB_F64) { VEXB_LANES tos[k].f = __dadd_rn(st[d - 2][k].f, tos[k].f); }
+                else { VEXB_LANES tos[k] = binary_op(op, t, st[d - 2][k], tos[k]); }
+                --d; break;
+            case VEXB_OP_SUB:
+                if (t == VEXB_F64) { VEXB_LANES tos[k].f = __dsub_rn(st[d - 2][k].f, tos[k].f); }
+                else { VEXB_LANES tos[k] = binary_op(op, t, st[d - 2][k], tos[k]); }
+                --d; break;
+            case VEXB_OP_MUL:
+                if (t == VEXB_F64) { VEXB_LANES tos[k].f = __dmul_rn(st[d - 2][k].f, tos[k].f); }
+                else { VEXB_LANES tos[k] = binary_op(op, t, st[d - 2][k], tos[k]); }
+                --d; break;
+            case VEXB_OP_DIV:
+                if (t == VEXB_F64) { VEXB_LANES tos[k].f = __ddiv_rn(st[d - 2][k].f, tos[k].f); }
+                else { VEXB_LANES tos[k] = binary_op(op, t, st[d - 2][k], tos[k]); }
+                --d; break;
+            case VEXB_OP_SELECT:
+                VEXB_LANES tos[k] = (st[d - 3][k].i != 0) ? st[d - 2][k] : tos[k];
+                d -= 2; break;
+            case VEXB_OP_FMA:
+                if (t == VEXB_F32) { VEXB_LANES tos[k].f = (double)__fmaf_rn((float)st[d - 3][k].f, (float)st[d - 2][k].f, (float)tos[k].f); }
+                else { VEXB_LANES tos[k].f = __fma_rn(st[d - 3][k].f, st[d - 2][k].f, tos[k].f); }
+                d -= 2; break;
+            default:
+                if ((op >= VEXB_OP_MOD && op <= VEXB_OP_LOR) || (op >= VEXB_OP_POW && op <= VEXB_OP_FMAX)) {
+                    VEXB_LANES tos[k] = binary_op(op, t, st[d - 2][k], tos[k]);
+                    --d;
+                } else {
+                    VEXB_LANES tos[k] = unary_op(op, t, tos[k]);
+                }
+                break;
         }
     }
+#undef VEXB_LANES
 #pragma unroll
     for (int k = 0; k < U; ++k) out[k] = tos[k];
 }

@@ -226,7 +226,7 @@ static bool launch_rsweep_shape(int sh, int op, int blocks, cudaStream_t st, con
 template <class T>
 static void launch_rinterp(int op, int blocks, cudaStream_t st, const vexb_expr &e, int dtype, size_t n, size_t off, void *ws, void *res) {
     switch (op) {
-#define C(OP) case OP: reduce_interp_kernel<OP, T, 2><<<blocks, 256, 0, st>>>(e, dtype, n, off, ws, (T *)res); break;
+#define C(OP) case OP: reduce_interp_kernel<OP, T, 4><<<blocks, 256, 0, st>>>(e, dtype, n, off, ws, (T *)res); break;
         C(VEXB_SUM) C(VEXB_SUM_KAHAN) C(VEXB_MAX) C(VEXB_MIN) C(VEXB_MINMAX)
 #undef C
     }
@@ -281,7 +281,7 @@ extern "C" int vexb_reduce(int dev, void *stream, const vexb_expr *expr, int dty
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = sm_count(dev);
-    long bps = param("reduce.blocks_per_sm", 4);
+    long bps = param("reduce.blocks_per_sm", 8);
     if (bps < 1) bps = 1; if (bps > kMaxBlocksPerSm) bps = kMaxBlocksPerSm;
     const size_t cap = (size_t)sms * (size_t)bps;
 
@@ -300,7 +300,7 @@ extern "C" int vexb_reduce(int dev, void *stream, const vexb_expr *expr, int dty
             if (launched) { VEXB_LAUNCHED(); return VEXB_OK; }
         }
     }
-    size_t want = (n + 511) / 512;
+    size_t want = (n + 1023) / 1024;
     const int blocks = (int)(want < cap ? want : cap);
     switch (dtype) {
         case VEXB_F64: launch_rinterp<double>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result); break;
