@@ -1,7 +1,6 @@
-"""Parameter sweeps on one GPU (run under gpurun): SpMV tile sizes / formats, sweep grid sizes."""
+"""Parameter sweeps on one GPU (run under gpurun): SpMV kernel variants / tile sizes / formats, vector kernels."""
 import json
 import sys
-import time
 from pathlib import Path
 
 import numpy as np
@@ -13,9 +12,10 @@ from vexcl_b200 import gen, _lib as L
 from vexcl_b200.api import Event
 
 ctx = vx.Context([0])
+VARIANT = {0: "csr-tma", 1: "csr-pipe", 2: "csr-direct"}
 
 
-def timeit(fn, reps=50, warm=5):
+def timeit(fn, reps=100, warm=5):
     for _ in range(warm):
         fn()
     ctx.finish()
@@ -27,30 +27,40 @@ def timeit(fn, reps=50, warm=5):
     return e0.elapsed_ms(e1) / reps
 
 
-def spmv_sweep(dim, nx, label):
-    row, col, val = gen.poisson_strip(dim, nx)
+def spmv_sweep(row, col, val, label, cfgs=None):
     N = row.size - 1
     nnz = int(row[-1])
     nbytes = gen.spmv_bytes(N, N, nnz)
     x, y = vx.vector(ctx, N), vx.vector(ctx, N)
     x.assign(vx.ElementIndex() * 1e-9 + 0.5)
-    res = []
-    cfgs = [(vx.FMT_HELL, 0, 0, 0, 0, 1)]
-    cfgs += [(vx.FMT_CSR, tn, tr, 0, 0, 0) for (tn, tr) in ((1536, 384), (2048, 512), (2560, 512), (3072, 768))]
-    cfgs += [(vx.FMT_CSR, tn, tr, st, 0, 1) for (tn, tr) in ((1024, 256), (2048, 512)) for st in (2, 3)]
-    for fmt, tn, tr, stages, cps, pipe in cfgs:
-        if fmt == vx.FMT_CSR:
-            vx.set_param("spmv.tile_nnz", tn); vx.set_param("spmv.tile_rows", tr); vx.set_param("spmv.pipeline", pipe)
-            vx.set_param("spmv.stages", stages or 4); vx.set_param("spmv.ctas_per_sm", cps)
-        A = vx.SpMat(ctx, N, N, row, col, val, fmt)
-        ms = timeit(lambda: A.apply(x, y, 1.0, False))
-        ms_app = timeit(lambda: A.apply(x, y, 1.0, True))
-        r = dict(case=label, fmt="hell" if fmt == vx.FMT_HELL else ("csr-pipe" if pipe else "csr-1shot"), tile_nnz=tn, tile_rows=tr, stages=stages, cps=cps, ms=ms, gbs=nbytes / ms / 1e6,
-                 ms_append=ms_app, gbs_append=(nbytes + 8 * N) / ms_app / 1e6, n_tiles=int(A.info().loc.n_tiles))
+    if cfgs is None:
+        cfgs = [("hell", 0, 0, 0)]
+        cfgs += [("csr", 0, tn, tr) for (tn, tr) in ((2048, 512),)]
+        cfgs += [("csr", 2, tn, tr) for (tn, tr) in ((1024, 256), (1536, 384), (2048, 512), (2048, 1024))]
+    for fmt, variant, tn, tr in cfgs:
+        if fmt == "csr":
+            vx.set_param("spmv.tile_nnz", tn); vx.set_param("spmv.tile_rows", tr); vx.set_param("spmv.kernel", variant)
+        A = vx.SpMat(ctx, N, N, row, col, val, vx.FMT_HELL if fmt == "hell" else vx.FMT_CSR)
+        ms = min(timeit(lambda: A.apply(x, y, 1.0, False)) for _ in range(3))
+        ms_app = min(timeit(lambda: A.apply(x, y, 1.0, True)) for _ in range(2))
+        r = dict(case=label, fmt="hell" if fmt == "hell" else VARIANT[variant], tile_nnz=tn, tile_rows=tr, ms=ms, gbs=nbytes / ms / 1e6,
+                 gbs_append=(nbytes + 8 * N) / ms_app / 1e6)
         print(json.dumps(r), flush=True)
-        res.append(r)
         del A
-    return res
+
+
+def random_rows(n, m, avg, seed):
+    """Irregular matrix: row widths U[0, 2*avg], sorted random columns within a band of 64*avg around the diagonal."""
+    rng = np.random.default_rng(seed)
+    w = rng.integers(0, 2 * avg + 1, n)
+    row = np.concatenate([[0], np.cumsum(w)]).astype(np.int64)
+    base = np.repeat(np.arange(n, dtype=np.int64), w)
+    off = rng.integers(-32 * avg, 32 * avg + 1, base.size)
+    col = np.clip(base + off, 0, m - 1)
+    # sort columns within rows
+    key = base * (m + 1) + col
+    col = col[np.argsort(key, kind="stable")]
+    return row, col, rng.random(col.size)
 
 
 def vec_sweep():
@@ -59,37 +69,26 @@ def vec_sweep():
     for v in (a, b, c, d):
         v.assign(vx.ElementIndex() * 1e-8 + 0.25)
     s = vx.Reductor(ctx, np.float64, L.SUM)
-    for bps in (2, 4, 6, 8, 12, 16, 32):
-        for persistent in (1, 0):
-            vx.set_param("sweep.blocks_per_sm", bps); vx.set_param("sweep.persistent", persistent)
-            ms = timeit(lambda: a.assign(b + c * d), reps=30)
-            ms2 = timeit(lambda: a.assign(0.5 * a + b), reps=30)
-            print(json.dumps(dict(case="a=b+c*d", bps=bps, persistent=persistent, ms=ms, gbs=32 * n / ms / 1e6, saxpy_gbs=24 * n / ms2 / 1e6)), flush=True)
-            if not persistent:
-                break
-    vx.set_param("sweep.blocks_per_sm", 8); vx.set_param("sweep.persistent", 1)
-    for bps in (2, 4, 8, 16):
-        vx.set_param("reduce.blocks_per_sm", bps)
-        ms = timeit(lambda: s(a * b), reps=30)
-        print(json.dumps(dict(case="sum(a*b)", bps=bps, ms=ms, gbs=16 * n / ms / 1e6)), flush=True)
-    vx.set_param("reduce.blocks_per_sm", 4)
+    for name, fn, bpe in (("a=b+c*d", lambda: a.assign(b + c * d), 32), ("a+=b+c*d", lambda: a.__iadd__(b + c * d), 40),
+                          ("a=alpha*a+b", lambda: a.assign(0.5 * a + b), 24), ("sum(a*b)", lambda: s(a * b), 16)):
+        ms = timeit(fn, reps=30)
+        print(json.dumps(dict(case=name, ms=ms, gbs=bpe * n / ms / 1e6)), flush=True)
     vx.set_param("eval.force_interp", 1)
-    for bps in (4, 6, 8):
-        vx.set_param("interp.blocks_per_sm", bps)
-        ms = timeit(lambda: a.assign(b + c * d), reps=20)
-        print(json.dumps(dict(case="interp a=b+c*d", bps=bps, ms=ms, gbs=32 * n / ms / 1e6)), flush=True)
-    ms = timeit(lambda: s(a * b), reps=20)
-    print(json.dumps(dict(case="interp sum(a*b)", ms=ms, gbs=16 * n / ms / 1e6)), flush=True)
-    ms = timeit(lambda: a.assign(vx.sin(b) * c + vx.sqrt(d)), reps=20)
-    print(json.dumps(dict(case="interp sin(b)*c+sqrt(d)", ms=ms, gbs=32 * n / ms / 1e6)), flush=True)
+    for name, fn, bpe in (("interp a=b+c*d", lambda: a.assign(b + c * d), 32), ("interp sum(a*b)", lambda: s(a * b), 16),
+                          ("interp sin(b)*c+sqrt(d)", lambda: a.assign(vx.sin(b) * c + vx.sqrt(d)), 32)):
+        ms = timeit(fn, reps=20)
+        print(json.dumps(dict(case=name, ms=ms, gbs=bpe * n / ms / 1e6)), flush=True)
     vx.set_param("eval.force_interp", 0)
 
 
 if __name__ == "__main__":
     what = sys.argv[1:] or ["spmv2d", "vec"]
     if "spmv2d" in what:
-        spmv_sweep(2, 3162, "poisson2d_3162")
+        spmv_sweep(*gen.poisson_strip(2, 3162), "poisson2d_3162")
     if "spmv3d" in what:
-        spmv_sweep(3, 256, "poisson3d_256")
+        spmv_sweep(*gen.poisson_strip(3, 256), "poisson3d_256")
+    if "irregular" in what:
+        spmv_sweep(*random_rows(4_000_000, 4_000_000, 12, 1), "random_avg12")
+        spmv_sweep(*random_rows(1_000_000, 1_000_000, 60, 2), "random_avg60")
     if "vec" in what:
         vec_sweep()

@@ -179,6 +179,99 @@ __global__ void __launch_bounds__(256) csr_stream_kernel(const int2 *__restrict_
     }
 }
 
+// ---- register-staged version of the stream kernel ------------------------------------------------
+// Same tiles, same two phases, but val / col go from HBM straight into registers (coalesced 8-byte
+// and 4-byte loads, L1 no-allocate), and only the products pass through shared memory.  Shared memory
+// per CTA drops from 26.8 KB to 16 KB, so L1 keeps ~150 KB for the x gathers (the TMA version leaves it
+// ~14 KB), and the bytes in flight live in the register file instead of the staging buffers.
+constexpr int kDirectThreads = 256;
+constexpr int kDirectPerThread = 8;                   // tile_nnz <= 2048
+
+template <class T>
+__global__ void __launch_bounds__(kDirectThreads, 5) csr_direct_kernel(const int2 *__restrict__ tile, const int *__restrict__ rowptr,
+                                                                        const int *__restrict__ col, const T *__restrict__ val,
+                                                                        const T *__restrict__ x, T *y, T alpha, int append,
+                                                                        const int *__restrict__ row_ids) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    T *prod = reinterpret_cast<T *>(smem);
+    const int tid = threadIdx.x;
+    const int2 t0 = __ldg(tile + blockIdx.x), t1 = __ldg(tile + blockIdx.x + 1);
+    const int r0 = t0.x, nr = t1.x - t0.x;
+    const int j0 = t0.y, cnt = t1.y - t0.y;
+    if (nr <= 0) return;
+    const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
+
+    if (cnt > kDirectThreads * kDirectPerThread) {
+        // one long row: the whole CTA strides over it
+        T s = T(0);
+        for (int j = j0 + tid; j < j0 + cnt; j += kDirectThreads) s = t_add<T>(s, t_mul<T>(ldg_stream(val + j, stream), ldg_keep(x + ldg_stream(col + j, stream), keep)));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s = t_add<T>(s, __shfl_down_sync(0xffffffffu, s, off));
+        if ((tid & 31) == 0) prod[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            T tot = prod[0];
+            for (int w = 1; w < kDirectThreads / 32; ++w) tot = t_add<T>(tot, prod[w]);
+            store_y<T>(y, row_ids ? (size_t)row_ids[r0] : (size_t)r0, tot, alpha, append);
+        }
+        return;
+    }
+
+    // row pointers of the (up to two) rows this thread will sum in phase B: issued first, needed last
+    int ra[2] = {0, 0}, rb[2] = {0, 0};
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int r = tid + p * kDirectThreads;
+        if (r < nr) { ra[p] = __ldg(rowptr + r0 + r); rb[p] = __ldg(rowptr + r0 + r + 1); }
+    }
+    // this thread's nonzeros j0 + tid + k*256: all loads issued back to back
+    int c[kDirectPerThread]; T v[kDirectPerThread]; T xv[kDirectPerThread];
+#pragma unroll
+    for (int k = 0; k < kDirectPerThread; ++k) {
+        const int j = tid + k * kDirectThreads;
+        if (j < cnt) { c[k] = ldg_stream(col + j0 + j, stream); v[k] = ldg_stream(val + j0 + j, stream); }
+    }
+#pragma unroll
+    for (int k = 0; k < kDirectPerThread; ++k) {
+        const int j = tid + k * kDirectThreads;
+        xv[k] = (j < cnt) ? ldg_keep(x + c[k], keep) : T(0);
+    }
+#pragma unroll
+    for (int k = 0; k < kDirectPerThread; ++k) {
+        const int j = tid + k * kDirectThreads;
+        if (j < cnt) prod[j] = t_mul<T>(v[k], xv[k]);
+    }
+    __syncthreads();
+    // phase B: row sums in storage order
+    if (cnt <= 12 * nr) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int r = tid + p * kDirectThreads;
+            if (r < nr) {
+                T s = T(0);
+                for (int j = ra[p] - j0; j < rb[p] - j0; ++j) s = t_add<T>(s, prod[j]);
+                store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, s, alpha, append);
+            }
+        }
+        for (int r = tid + 2 * kDirectThreads; r < nr; r += kDirectThreads) {
+            const int a = __ldg(rowptr + r0 + r) - j0, b = __ldg(rowptr + r0 + r + 1) - j0;
+            T s = T(0);
+            for (int j = a; j < b; ++j) s = t_add<T>(s, prod[j]);
+            store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, s, alpha, append);
+        }
+    } else {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int r = warp; r < nr; r += kDirectThreads / 32) {
+            const int a = __ldg(rowptr + r0 + r) - j0, b = __ldg(rowptr + r0 + r + 1) - j0;
+            T s = T(0);
+            for (int j = a + lane; j < b; j += 32) s = t_add<T>(s, prod[j]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s = t_add<T>(s, __shfl_down_sync(0xffffffffu, s, off));
+            if (lane == 0) store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, s, alpha, append);
+        }
+    }
+}
+
 // ---- persistent, warp-specialised, multi-stage version of the stream kernel ---------------------
 // One producer warp keeps up to `stages` tiles in flight with TMA bulk copies (full/empty
 // mbarrier ring); eight consumer warps do phase A / phase B of the oldest tile meanwhile, so
@@ -330,6 +423,9 @@ __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w
 #pragma unroll
         for (int j = 0; j < W; ++j) if (c[j] != -1) sum = t_add<T>(sum, t_mul<T>(v[j], xv[j]));
     } else {
+        // any width: plain dependent loop.  Measured faster on irregular matrices than batching 4 columns
+        // (4.2 vs 3.3 TB/s effective at average width 12): occupancy hides the latency, and a padded slot
+        // (column -1) costs 4 bytes, not 12, because its value is never fetched.
         for (int j = 0; j < w_dyn; ++j) {
             const int c = ldg_stream(ell_col + i + (size_t)j * pitch, stream);
             if (c != -1) sum = t_add<T>(sum, t_mul<T>(ldg_stream(ell_val + i + (size_t)j * pitch, stream), ldg_keep(x + c, keep)));
@@ -378,12 +474,15 @@ template <class T>
 static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col, std::vector<T> &val, int fmt) {
     const size_t n = A->nrows_stored;
     if (fmt == VEXB_FMT_AUTO) {
-        // ELL when padding is small; otherwise the CSR stream kernel.
+        // As the reference does on GPUs (spmat.hpp:98-103): hybrid ELL.  Measured on B200 it beats the CSR
+        // stream kernel even with 40 % padding (profiles/r01_tune_spmv_variants.jsonl); only when the
+        // padded storage would exceed 3x the nonzeros (a few very long rows among many short ones are
+        // already caught by the CSR tail) does the CSR stream kernel take over.
         const size_t w = hell_width(rowptr, n);
         size_t tail = 0;
         for (size_t i = 0; i < n; ++i) { const size_t rw = rowptr[i + 1] - rowptr[i]; if (rw > w) tail += rw - w; }
         const double padded = (double)w * (double)((n + 15) / 16 * 16) + (double)tail;
-        fmt = (A->nnz > 0 && padded <= 1.1 * (double)A->nnz && tail == 0) ? VEXB_FMT_HELL : VEXB_FMT_CSR;
+        fmt = (A->nnz > 0 && padded <= 3.0 * (double)A->nnz) ? VEXB_FMT_HELL : VEXB_FMT_CSR;
     }
     A->fmt = fmt;
     if (fmt == VEXB_FMT_CSR) {
@@ -445,7 +544,14 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
         if (!append) { zero_rows_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, n, A->row_ids); VEXB_LAUNCHED(); }
         return VEXB_OK;
     }
-    if (A->fmt == VEXB_FMT_CSR && param("spmv.pipeline", 0)) {
+    // spmv.kernel: 0 = TMA-staged one-shot tiles, 1 = persistent TMA pipeline, 2 = register-staged tiles
+    const long variant = param("spmv.kernel", param("spmv.pipeline", 0) ? 1 : 0);
+    if (A->fmt == VEXB_FMT_CSR && variant == 2 && A->tile_nnz <= (size_t)kDirectThreads * kDirectPerThread) {
+        const size_t smem = std::max<size_t>(A->tile_nnz, 64) * sizeof(T);
+        csr_direct_kernel<T><<<(unsigned)A->n_tiles, kDirectThreads, smem, st>>>(A->tile, A->rowptr, A->col, (const T *)A->val, x, y,
+                                                                                alpha, append, A->row_ids);
+        VEXB_LAUNCHED();
+    } else if (A->fmt == VEXB_FMT_CSR && variant == 1) {
         long stages = param("spmv.stages", 4);
         stages = std::max(2l, std::min(stages, 16l));
         const size_t stage_bytes = ((A->tile_nnz + 8) * sizeof(T) + (A->tile_nnz + 8) * 4 + (A->tile_rows + 12) * 4 + 127) & ~(size_t)127;
