@@ -286,3 +286,29 @@ void orc_cpp_spmv(size_t N, const int64_t *row, const int64_t *col, const double
         Y[i] += s;
     }
 }
+
+/* ---- timing helpers (bench.py's CPU baseline only) -------------------------------------------
+ * First-touch placement: on a multi-socket host a buffer filled by one thread lives on one NUMA node
+ * and every other core reads it remotely.  These clones are written by the same static work-group ->
+ * thread mapping the kernels above use, so each thread's chunk is local to it, which is what an
+ * OpenCL CPU runtime's own buffers would look like after a first kernel has written them.
+ * row_chunks != NULL: elements are nonzeros, chunked by the ROW ranges of the groups. */
+void *orc_numa_clone(const void *src, size_t n, size_t elem, const int64_t *row, size_t nrows, int G) {
+    char *dst = (char *)malloc(n * elem + 64);
+    if (!dst) return NULL;
+#pragma omp parallel for schedule(static)
+    for (int g = 0; g < G; ++g) {
+        size_t lo, hi;
+        if (row) { size_t rl, rh; chunk_bounds(nrows, G, g, &rl, &rh); lo = (size_t)(row[rl] - row[0]); hi = (size_t)(row[rh] - row[0]); }
+        else chunk_bounds(n, G, g, &lo, &hi);
+        if (hi > lo) memcpy(dst + lo * elem, (const char *)src + lo * elem, (hi - lo) * elem);
+    }
+    return dst;
+}
+
+void orc_free(void *p) { free(p); }
+
+/* One timed pass on raw (cloned) pointers. */
+void orc_csr_spmv_raw(size_t n, const int64_t *row, const int64_t *col, const double *val, const double *x, double *y, int G) {
+    orc_csr_spmv(n, row, col, val, x, y, 1.0, 0, 0, G);
+}
