@@ -47,6 +47,8 @@ def lib():
         L = C.CDLL(str(_LIB_PATH))
         dp, ip, sz = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_size_t
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_threads(usable_cpus())      # respect the container's CPU quota (cgroup cpu.max), not just the CPU count
         L.orc_partition.argtypes = [sz, C.c_int, dp, C.POINTER(sz)]
         L.orc_uniform_real.argtypes = [C.c_uint32, sz, dp]
         L.orc_poisson_sizes.argtypes = [C.c_int, sz, C.POINTER(sz), C.POINTER(sz)]
@@ -88,14 +90,37 @@ def _i64(a):
     return np.ascontiguousarray(a, dtype=np.int64)
 
 
+def usable_cpus() -> int:
+    """Host threads this process can really run: the smaller of the visible CPUs (affinity mask) and the
+    cgroup CPU quota (cpu.max = "quota period"), e.g. 16 on a 128-thread host leased with a 16-CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = Path(path).read_text().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, -(-int(txt[0]) // int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    n = min(n, max(1, -(-q // int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text()))))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
 
 
 def default_groups() -> int:
     """8 * compute units (vexcl/backend/opencl/kernel.hpp:166-171); a CPU device exposes one
-    compute unit per hardware thread."""
-    return 8 * (os.cpu_count() or 1)
+    compute unit per usable hardware thread."""
+    return 8 * usable_cpus()
 
 
 # ---------------------------------------------------------------------------- partition
