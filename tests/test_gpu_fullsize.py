@@ -87,7 +87,10 @@ def test_config2_poisson2d_full_size(request, ctxname, fmt):
         assert np.array_equal(got, want)                       # one slice: same order of operations, no contraction
     # (3) linearity: A(2x) = 2 A x exactly (power-of-two scaling), y += A x doubles y
     y += A * x
-    assert np.array_equal(y.read(), 2 * got)
+    if ctx.nparts == 1:
+        assert np.array_equal(y.read(), 2 * got)
+    else:                                                      # boundary rows: ((l + r) + l) + r, not 2 (l + r)
+        assert np.all(np.abs(y.read() - 2 * got) <= 1e-10 * mag)
     x.assign(2.0 * x)
     y.assign(A * x)
     assert np.array_equal(y.read(), 2 * got)
