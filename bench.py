@@ -212,7 +212,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.all_gather_object(out, np.asarray(arr))
             return out
 
-        ctx = vx.Context.distributed(rank, world, local_rank, uid[0], allgather)
+        ctx = vx.Context.distributed(rank, world, local_rank, uid[0], allgather, use_peer=not args.no_peer)
         tok = torch.zeros(1, device="cuda")
 
         def barrier():
@@ -506,6 +506,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="combine reductions with ncclAllReduce instead of the fused peer-memory exchange")
     ap.add_argument("--format", default="auto", choices=["auto", "csr", "hell"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -265,6 +265,34 @@ int vexb_graph_launch(vexb_graph *graph, void *stream);
 int vexb_graph_destroy(vexb_graph *graph);
 
 /* ------------------------------------------------------------------------
+ * Peer memory: a group of ranks (one per GPU) whose kernels write into each
+ * other's device memory over NVLink.  Used to fuse the combine of
+ * Reductor across GPUs into the reduction kernel itself (vexb_reduce_all):
+ * the last block of every rank pushes its value into all peers' mailboxes
+ * and folds what it received, in rank order -- one kernel, no NCCL call, no
+ * host (replaces reductor.hpp:412-436).
+ *   one process per GPU : vexb_peer_create (returns a 64-byte CUDA IPC handle),
+ *                         the launcher all-gathers the handles (rank order),
+ *                         vexb_peer_connect maps the other ranks' mailboxes;
+ *   one process, n GPUs : vexb_peer_create_all (peer access, distinct devices).
+ * A rank that never shows up makes the waiting kernel give up after a few
+ * seconds and set an error word (vexb_peer_error != 0) instead of hanging.
+ * ---------------------------------------------------------------------- */
+typedef struct vexb_peer vexb_peer;
+#define VEXB_IPC_HANDLE_BYTES 64
+int vexb_peer_create(int dev, int rank, int nranks, vexb_peer **peer, void *handle64);
+int vexb_peer_connect(vexb_peer *peer, const void *handles /* nranks * 64 bytes, rank order */);
+int vexb_peer_create_all(int ndev, const int *devs, vexb_peer **peers /* ndev out */);
+int vexb_peer_destroy(vexb_peer *peer);
+int vexb_peer_error(vexb_peer *peer, unsigned long long *epoch_of_timeout /* 0 = none */);
+/* In-place all-reduce of one value (two for VEXB_MINMAX) per rank. */
+int vexb_peer_allreduce(vexb_peer *peer, void *stream, void *d_buf, int dtype, int op);
+/* vexb_reduce + the combine across the peer group in the same kernel; every rank ends with the
+ * same bits in d_result.  peer == NULL (or a group of one) is plain vexb_reduce. */
+int vexb_reduce_all(int dev, void *stream, const vexb_expr *expr, int dtype, size_t n,
+                    size_t index_offset, int op, void *d_result, void *d_workspace, vexb_peer *peer);
+
+/* ------------------------------------------------------------------------
  * Halo plan (host only; no GPU needed): who sends which x entries to whom.
  * Input: column partition and, for every part d, the sorted unique list of
  * global column ids outside [col_part[d], col_part[d+1]) referenced by the

@@ -68,6 +68,42 @@ def test_nccl_reduce_and_halo_single_process(ctxn):
     assert np.all(np.abs(y.read() - want) <= 1e-10 * np.abs(want) + 1e-300)
 
 
+def test_fused_reduce_allreduce_over_peer_memory(built):
+    """vexb_reduce_all: the last block of each rank's reduction kernel exchanges partials through peer
+    mailboxes (no NCCL); every rank must end with the same bits, and the sum must match the oracle."""
+    n = ndev()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ctx = vx.Context(list(range(min(n, 8))), use_peer=True)
+    N = 1_000_003
+    X = oracle.uniform_real(5, N)
+    x = vx.vector(ctx, X)
+    ref = oracle.kahan_sum(X)
+    s = vx.Reductor(ctx, np.float64, L.SUM)
+    for _ in range(5):                                           # epochs advance, parity alternates
+        assert abs(s(x) - ref) <= 1e-10 * abs(ref)
+    assert vx.Reductor(ctx, np.float64, L.MAX)(x) == X.max()
+    assert vx.Reductor(ctx, np.float64, L.MINMAX)(x) == (X.min(), X.max())
+    assert vx.Reductor(ctx, np.int64, L.SUM)(x > 0.25) == int((X > 0.25).sum())
+    from vexcl_b200.api import DeviceScalar
+    d = DeviceScalar(ctx)
+    s.device(x * x, d)
+    ctx.finish()
+    vals = []
+    for k in ctx.local:                                          # identical bits on every device
+        h = np.empty(1)
+        L.check(L.lib().vexb_d2h(ctx.devs[k], h.ctypes.data, d.bufs[k], 8, ctx.streams[k], 1))
+        vals.append(h[0])
+    assert len(set(vals)) == 1 and abs(vals[0] - np.dot(X, X)) <= 1e-10 * np.dot(X, X)
+    # an empty slice still takes part (n = 1 over several devices)
+    one = vx.vector(ctx, 1)
+    one.assign(42.0)
+    assert s(one) == 42.0
+    err = __import__("ctypes").c_uint64(7)
+    L.check(L.lib().vexb_peer_error(ctx.peers[0], __import__("ctypes").byref(err)))
+    assert err.value == 0
+
+
 def test_copy_engine_halo_without_nccl(built):
     if ndev() < 2:
         pytest.skip("needs >= 2 GPUs")

@@ -121,6 +121,11 @@ def lib():
         "vexb_comm_barrier": ([i, P(vp), P(vp)], i),
         "vexb_graph_begin": ([i, vp], i), "vexb_graph_end": ([i, vp, P(vp)], i),
         "vexb_graph_launch": ([vp, vp], i), "vexb_graph_destroy": ([vp], i),
+        "vexb_peer_create": ([i, i, i, P(vp), vp], i), "vexb_peer_connect": ([vp, vp], i),
+        "vexb_peer_create_all": ([i, P(i), P(vp)], i), "vexb_peer_destroy": ([vp], i),
+        "vexb_peer_error": ([vp, P(C.c_uint64)], i),
+        "vexb_peer_allreduce": ([vp, vp, vp, i, i], i),
+        "vexb_reduce_all": ([i, vp, P(Expr), i, sz, sz, i, vp, vp, vp], i),
         "vexb_strip_ghost_cols": ([sz, vp, i, vp, i, sz, sz, vp, P(sz)], i),
         "vexb_halo_plan_create": ([i, P(sz), vp, P(sz), P(vp)], i),
         "vexb_halo_plan_destroy": ([vp], i),

@@ -66,8 +66,9 @@ def partition(n: int, nparts: int, weights=None) -> np.ndarray:
 # ------------------------------------------------------------------------------------------- Context
 class Context:
     """A list of (device, stream) pairs, one per partition slot."""
+    use_peer_reduce = True          # combine reductions through peer memory when a peer group exists
 
-    def __init__(self, devices: Sequence[int] = (0,), use_nccl: Optional[bool] = None, weights=None):
+    def __init__(self, devices: Sequence[int] = (0,), use_nccl: Optional[bool] = None, weights=None, use_peer: bool = False):
         lib = L.lib()
         L.check(lib.vexb_init())
         self.nparts = len(devices)
@@ -91,11 +92,19 @@ class Context:
             out = (C.c_void_p * self.nparts)()
             L.check(lib.vexb_comm_create_all(self.nparts, arr, out))
             self.comms = {k: C.c_void_p(out[k]) for k in range(self.nparts)}
+        self.peers = None
+        if use_peer and self.nparts > 1:
+            if not distinct:
+                raise ValueError("peer groups need one distinct device per part")
+            arr = (C.c_int * self.nparts)(*devices)
+            out = (C.c_void_p * self.nparts)()
+            L.check(lib.vexb_peer_create_all(self.nparts, arr, out))
+            self.peers = {k: C.c_void_p(out[k]) for k in range(self.nparts)}
         self._ws = {}
 
     @classmethod
     def distributed(cls, rank: int, nranks: int, dev: int, unique_id: bytes,
-                    allgather: Callable[[np.ndarray], list]):
+                    allgather: Callable[[np.ndarray], list], use_peer: bool = True):
         """One process per device.  `unique_id`: the 128 bytes produced by rank 0's
         comm_unique_id() and broadcast by the launcher; `allgather(arr)` returns the list of every
         rank's int64 array (used once, at SpMat construction, to share ghost column lists)."""
@@ -116,6 +125,16 @@ class Context:
             L.check(lib.vexb_comm_create_rank(dev, nranks, rank, buf, C.byref(c)))
             self.comms = {rank: c}
         self.allgather = allgather
+        self.peers = None
+        if nranks > 1 and use_peer:
+            # peer-memory group: exchange the CUDA IPC handles of the mailboxes through the launcher's all-gather
+            p = C.c_void_p()
+            h = C.create_string_buffer(64)
+            L.check(lib.vexb_peer_create(dev, rank, nranks, C.byref(p), h))
+            allh = allgather(np.frombuffer(h.raw, dtype=np.uint8).copy())
+            cat = b"".join(np.asarray(a, dtype=np.uint8).tobytes() for a in allh)
+            L.check(lib.vexb_peer_connect(p, C.create_string_buffer(cat, 64 * nranks)))
+            self.peers = {rank: p}
         self._ws = {}
         return self
 
@@ -564,11 +583,15 @@ class Reductor:
             ws, r = ctx.workspace(k)
             low = _Lowering(k, int(part[k]))
             low.lower(expr)
-            L.check(lib.vexb_reduce(ctx.devs[k], ctx.streams[k], C.byref(low.e), self.dtype, int(part[k + 1] - part[k]),
-                                    int(part[k]), self.kind, r, ws))
+            peer = ctx.peers[k] if (ctx.peers is not None and ctx.use_peer_reduce and ctx.nparts > 1) else None
+            L.check(lib.vexb_reduce_all(ctx.devs[k], ctx.streams[k], C.byref(low.e), self.dtype, int(part[k + 1] - part[k]),
+                                        int(part[k]), self.kind, r, ws, peer))
             res[k] = r
         out = np.empty(cnt, dtype=self.np_dtype)
-        if ctx.nparts > 1 and ctx.comms is not None:
+        if ctx.nparts > 1 and ctx.peers is not None and ctx.use_peer_reduce:
+            k = ctx.local[0]                                       # combined inside the kernel over peer memory
+            L.check(lib.vexb_reduce_fetch(ctx.devs[k], ctx.streams[k], res[k], self.dtype, cnt, out.ctypes.data))
+        elif ctx.nparts > 1 and ctx.comms is not None:
             # combine over NVLink (replaces the host fold, reductor.hpp:412-436)
             L.check(lib.vexb_comm_allreduce(len(ctx.local), ctx._arr(ctx.comms), ctx._arr(res), ctx._arr(ctx.streams),
                                             1, self.dtype, self.kind))
@@ -817,9 +840,11 @@ def _reduce_device(self, expr, out: DeviceScalar):
         ws, _ = ctx.workspace(k)
         low = _Lowering(k, int(part[k]))
         low.lower(expr)
-        L.check(lib.vexb_reduce(ctx.devs[k], ctx.streams[k], C.byref(low.e), self.dtype, int(part[k + 1] - part[k]),
-                                int(part[k]), self.kind, out.bufs[k], ws))
-    if ctx.nparts > 1:
+        # with a peer group the combine across GPUs happens inside the reduction kernel (no NCCL call)
+        peer = ctx.peers[k] if (ctx.peers is not None and ctx.use_peer_reduce) else None
+        L.check(lib.vexb_reduce_all(ctx.devs[k], ctx.streams[k], C.byref(low.e), self.dtype, int(part[k + 1] - part[k]),
+                                    int(part[k]), self.kind, out.bufs[k], ws, peer))
+    if ctx.nparts > 1 and not (ctx.peers is not None and ctx.use_peer_reduce):
         if ctx.comms is None:
             raise RuntimeError("device-resident reductions over several slots need a communicator (NCCL)")
         L.check(lib.vexb_comm_allreduce(len(ctx.local), ctx._arr(ctx.comms), ctx._arr(out.bufs), ctx._arr(ctx.streams),

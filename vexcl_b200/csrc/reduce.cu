@@ -11,6 +11,7 @@
 // for vexb_comm_allreduce or a single 8-byte D2H.
 #include "expr_eval.cuh"
 #include "shapes.cuh"
+#include "peer.cuh"
 #include <limits>
 
 namespace vexb {
@@ -67,8 +68,11 @@ struct ReduceWs {               // layout of d_workspace
     // followed by 2 * max_blocks values of 8 bytes
 };
 
+template <class T> __device__ __forceinline__ unsigned long long to_bits(T v) { unsigned long long u = 0; memcpy(&u, &v, sizeof(T)); return u; }
+template <class T> __device__ __forceinline__ T from_bits(unsigned long long u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
+
 template <int OP, class T>
-__device__ __forceinline__ void block_finish(Fold<OP, T> f, void *ws, T *result) {
+__device__ __forceinline__ void block_finish(Fold<OP, T> f, void *ws, T *result, const PeerArgs &pa) {
     __shared__ T sx[8], sy[8];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -106,14 +110,29 @@ __device__ __forceinline__ void block_finish(Fold<OP, T> f, void *ws, T *result)
     if (threadIdx.x == 0) {
         Fold<OP, T> b; b.x = sx[0]; b.y = sy[0];
         for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { Fold<OP, T> o; o.x = sx[w]; o.y = sy[w]; b.merge(o); }
-        result[0] = b.x;
-        if (OP == VEXB_MINMAX) result[1] = b.y;
+        sx[0] = b.x; sy[0] = b.y;
         *ticket = 0;
+    }
+    __syncthreads();
+    if (pa.nranks > 1) {
+        // combine across GPUs in the same kernel: one-hop exchange over NVLink peer memory (peer.cuh)
+        __shared__ unsigned long long px[VEXB_MAX_PEERS], py[VEXB_MAX_PEERS];
+        peer_exchange(pa, to_bits<T>(sx[0]), to_bits<T>(sy[0]), px, py);
+        if (threadIdx.x == 0) {
+            Fold<OP, T> b; b.x = from_bits<T>(px[0]); b.y = from_bits<T>(py[0]);
+            for (int r = 1; r < pa.nranks; ++r) { Fold<OP, T> o; o.x = from_bits<T>(px[r]); o.y = from_bits<T>(py[r]); b.merge(o); }
+            sx[0] = b.x; sy[0] = b.y;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        result[0] = sx[0];
+        if (OP == VEXB_MINMAX) result[1] = sy[0];
     }
 }
 
 template <int SH, int OP, class T, int U>
-__global__ void __launch_bounds__(256) reduce_sweep_kernel(SweepArgs a, size_t n, void *ws, T *result) {
+__global__ void __launch_bounds__(256) reduce_sweep_kernel(SweepArgs a, size_t n, void *ws, T *result, PeerArgs pa) {
     typedef Shape<SH> S;
     typedef Lanes<T> L;
     constexpr int E = L::E;
@@ -162,7 +181,7 @@ __global__ void __launch_bounds__(256) reduce_sweep_kernel(SweepArgs a, size_t n
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int j = 0; j < E; ++j) if (u || j) f.merge(acc[u][j]);
-    block_finish<OP, T>(f, ws, result);
+    block_finish<OP, T>(f, ws, result, pa);
 }
 
 template <class T> __device__ __forceinline__ T v_as(V v);
@@ -175,7 +194,7 @@ template <> __device__ __forceinline__ unsigned long long v_as<unsigned long lon
 
 template <int OP, class T, int U>
 __global__ void __launch_bounds__(256) reduce_interp_kernel(const __grid_constant__ vexb_expr e, int dtype, size_t n,
-                                                             size_t index_offset, void *ws, T *result) {
+                                                             size_t index_offset, void *ws, T *result, PeerArgs pa) {
     const int rt = program_result_type(e);
     Fold<OP, T> acc[U];
 #pragma unroll
@@ -192,7 +211,7 @@ __global__ void __launch_bounds__(256) reduce_interp_kernel(const __grid_constan
     Fold<OP, T> f = acc[0];
 #pragma unroll
     for (int k = 1; k < U; ++k) f.merge(acc[k]);
-    block_finish<OP, T>(f, ws, result);
+    block_finish<OP, T>(f, ws, result, pa);
 }
 
 template <int OP, class T>
@@ -205,18 +224,18 @@ __global__ void identity_kernel(T *result) {
 static const int kMaxBlocksPerSm = 16;
 
 template <int SH, class T>
-static void launch_rsweep(int op, int blocks, cudaStream_t st, const SweepArgs &a, size_t n, void *ws, void *res) {
+static void launch_rsweep(int op, int blocks, cudaStream_t st, const SweepArgs &a, size_t n, void *ws, void *res, const PeerArgs &pa) {
     switch (op) {
-#define C(OP) case OP: reduce_sweep_kernel<SH, OP, T, 2><<<blocks, 256, 0, st>>>(a, n, ws, (T *)res); break;
+#define C(OP) case OP: reduce_sweep_kernel<SH, OP, T, 2><<<blocks, 256, 0, st>>>(a, n, ws, (T *)res, pa); break;
         C(VEXB_SUM) C(VEXB_SUM_KAHAN) C(VEXB_MAX) C(VEXB_MIN) C(VEXB_MINMAX)
 #undef C
     }
 }
 
 template <class T>
-static bool launch_rsweep_shape(int sh, int op, int blocks, cudaStream_t st, const SweepArgs &a, size_t n, void *ws, void *res) {
+static bool launch_rsweep_shape(int sh, int op, int blocks, cudaStream_t st, const SweepArgs &a, size_t n, void *ws, void *res, const PeerArgs &pa) {
     switch (sh) {
-#define C(ID) case ID: launch_rsweep<ID, T>(op, blocks, st, a, n, ws, res); return true;
+#define C(ID) case ID: launch_rsweep<ID, T>(op, blocks, st, a, n, ws, res, pa); return true;
         C(SH_COPY) C(SH_MUL) C(SH_SQR) C(SH_SUB) C(SH_ABSDIFF)
 #undef C
         default: return false;
@@ -224,9 +243,9 @@ static bool launch_rsweep_shape(int sh, int op, int blocks, cudaStream_t st, con
 }
 
 template <class T>
-static void launch_rinterp(int op, int blocks, cudaStream_t st, const vexb_expr &e, int dtype, size_t n, size_t off, void *ws, void *res) {
+static void launch_rinterp(int op, int blocks, cudaStream_t st, const vexb_expr &e, int dtype, size_t n, size_t off, void *ws, void *res, const PeerArgs &pa) {
     switch (op) {
-#define C(OP) case OP: reduce_interp_kernel<OP, T, 4><<<blocks, 256, 0, st>>>(e, dtype, n, off, ws, (T *)res); break;
+#define C(OP) case OP: reduce_interp_kernel<OP, T, 4><<<blocks, 256, 0, st>>>(e, dtype, n, off, ws, (T *)res, pa); break;
         C(VEXB_SUM) C(VEXB_SUM_KAHAN) C(VEXB_MAX) C(VEXB_MIN) C(VEXB_MINMAX)
 #undef C
     }
@@ -271,13 +290,26 @@ extern "C" int vexb_reduce_identity(int dev, void *stream, int dtype, int op, vo
 
 extern "C" int vexb_reduce(int dev, void *stream, const vexb_expr *expr, int dtype, size_t n,
                            size_t index_offset, int op, void *d_result, void *d_workspace) {
+    return vexb_reduce_all(dev, stream, expr, dtype, n, index_offset, op, d_result, d_workspace, nullptr);
+}
+
+extern "C" int vexb_reduce_all(int dev, void *stream, const vexb_expr *expr, int dtype, size_t n,
+                               size_t index_offset, int op, void *d_result, void *d_workspace, vexb_peer *peer) {
+    PeerArgs pa; memset(&pa, 0, sizeof(pa));
+    if (peer && peer->nranks > 1) {
+        VEXB_CHECK(peer->dev == dev, "peer group lives on device %d, not %d", peer->dev, dev);
+        pa = peer->args();
+    }
     VEXB_CHECK(dtype >= VEXB_F64 && dtype <= VEXB_U64, "bad dtype %d", dtype);
     VEXB_CHECK(op >= VEXB_SUM && op <= VEXB_MINMAX, "bad reduce op %d", op);
     VEXB_CHECK(d_result && d_workspace, "d_result / d_workspace is NULL");
     if (op == VEXB_SUM_KAHAN && !dtype_is_float(dtype)) op = VEXB_SUM;
     vexb_expr e;
     VEXB_TRY(normalize_expr(expr, &e, n != 0));
-    if (n == 0) return vexb_reduce_identity(dev, stream, dtype, op, d_result);   // reductor.hpp:318-321
+    if (n == 0) {                                                               // reductor.hpp:318-321
+        VEXB_TRY(vexb_reduce_identity(dev, stream, dtype, op, d_result));
+        return pa.nranks > 1 ? vexb_peer_allreduce(peer, stream, d_result, dtype, op) : VEXB_OK;
+    }
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = sm_count(dev);
@@ -295,20 +327,20 @@ extern "C" int vexb_reduce(int dev, void *stream, const vexb_expr *expr, int dty
             const size_t E = dtype == VEXB_F64 ? 4 : 8;
             size_t want = (n / E + 511) / 512; if (want < 1) want = 1;
             const int blocks = (int)(want < cap ? want : cap);
-            bool launched = dtype == VEXB_F64 ? launch_rsweep_shape<double>(m.shape, op, blocks, st, a, n, d_workspace, d_result)
-                                              : launch_rsweep_shape<float>(m.shape, op, blocks, st, a, n, d_workspace, d_result);
+            bool launched = dtype == VEXB_F64 ? launch_rsweep_shape<double>(m.shape, op, blocks, st, a, n, d_workspace, d_result, pa)
+                                              : launch_rsweep_shape<float>(m.shape, op, blocks, st, a, n, d_workspace, d_result, pa);
             if (launched) { VEXB_LAUNCHED(); return VEXB_OK; }
         }
     }
     size_t want = (n + 1023) / 1024;
     const int blocks = (int)(want < cap ? want : cap);
     switch (dtype) {
-        case VEXB_F64: launch_rinterp<double>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result); break;
-        case VEXB_F32: launch_rinterp<float>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result); break;
-        case VEXB_I32: launch_rinterp<int>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result); break;
-        case VEXB_U32: launch_rinterp<unsigned>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result); break;
-        case VEXB_I64: launch_rinterp<long long>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result); break;
-        default:       launch_rinterp<unsigned long long>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result); break;
+        case VEXB_F64: launch_rinterp<double>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result, pa); break;
+        case VEXB_F32: launch_rinterp<float>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result, pa); break;
+        case VEXB_I32: launch_rinterp<int>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result, pa); break;
+        case VEXB_U32: launch_rinterp<unsigned>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result, pa); break;
+        case VEXB_I64: launch_rinterp<long long>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result, pa); break;
+        default:       launch_rinterp<unsigned long long>(op, blocks, st, e, dtype, n, index_offset, d_workspace, d_result, pa); break;
     }
     VEXB_LAUNCHED();
     return VEXB_OK;
