@@ -3,8 +3,9 @@
 /*
  * vex::Reductor<T, RDC> (vexcl/reductor.hpp:289-439).  The reference reduces each slice to 8*SM
  * partials, copies them to the host and folds them there (:412-436).  Here each device leaves ONE
- * value in device memory (vexb_reduce: warp-shuffle fold, last block combines); with several
- * distinct devices the values are combined by ncclAllReduce over NVLink, and one 8-byte copy
+ * value in device memory (vexb_reduce_all: warp-shuffle fold, last block combines); with several
+ * distinct devices the last blocks also exchange their values through peer memory over NVLink
+ * inside the same kernel (ncclAllReduce if peer access is unavailable), and one 8-byte copy
  * brings the result back.  When the slices share a device (the reference's own single-GPU test
  * trick) or NCCL is unavailable, the nparts values are folded on the host in device order.
  */
@@ -50,6 +51,31 @@ inline std::shared_ptr<comm_set> communicators(const std::vector<backend::comman
     return cs;
 }
 
+/// Peer-memory groups (mailboxes mapped between the devices) for a queue list; empty when not applicable.
+struct peer_set {
+    std::vector<vexb_peer*> peers;
+    ~peer_set() { for (auto p : peers) vexb_peer_destroy(p); }
+};
+inline std::shared_ptr<peer_set> peer_group(const std::vector<backend::command_queue> &queue) {
+    static std::mutex mx;
+    static std::map<std::vector<int>, std::shared_ptr<peer_set>> cache;
+    std::vector<int> devs;
+    for (auto &q : queue) devs.push_back(q.ordinal());
+    std::lock_guard<std::mutex> lock(mx);
+    auto it = cache.find(devs);
+    if (it != cache.end()) return it->second;
+    auto ps = std::make_shared<peer_set>();
+    std::vector<int> sorted(devs);
+    std::sort(sorted.begin(), sorted.end());
+    const bool distinct = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
+    if (devs.size() > 1 && devs.size() <= 16 && distinct && !std::getenv("VEXCL_NO_PEER")) {
+        ps->peers.resize(devs.size(), nullptr);
+        if (vexb_peer_create_all(static_cast<int>(devs.size()), devs.data(), ps->peers.data()) != VEXB_OK) ps->peers.clear();
+    }
+    cache[devs] = ps;
+    return ps;
+}
+
 template <class T, class RDC> struct reduce_result { typedef T type; static T make(const T *v) { return v[0]; } };
 template <class T> struct reduce_result<T, MIN_MAX> { typedef vec2<T> type; static type make(const T *v) { type r; r.s[0] = v[0]; r.s[1] = v[1]; return r; } };
 
@@ -90,14 +116,19 @@ class Reductor {
             if (!p.sized || p.size == 0) return detail::reduce_result<ScalarType, RDC>::make(out);   // reductor.hpp:318-321
             if (p.part.empty()) p.part = vex::partition(p.size, queue);                                // :323-325
 
+            // distinct devices: the combine across GPUs happens inside the reduction kernel (peer memory)
+            auto ps = queue.size() > 1 ? detail::peer_group(queue) : std::shared_ptr<detail::peer_set>();
+            const bool fused = ps && !ps->peers.empty();
             for (unsigned d = 0; d < queue.size(); ++d) {
                 detail::ir_builder b(d);
                 expr.lower(b);
-                VEXB_CHECKED(vexb_reduce(queue[d].ordinal(), queue[d].raw(), &b.e, dt, p.part_size(d), p.part_start(d),
-                                         op, res[d].raw(), ws[d].raw()));
+                VEXB_CHECKED(vexb_reduce_all(queue[d].ordinal(), queue[d].raw(), &b.e, dt, p.part_size(d), p.part_start(d),
+                                             op, res[d].raw(), ws[d].raw(), fused ? ps->peers[d] : nullptr));
             }
-            auto cs = queue.size() > 1 ? detail::communicators(queue) : std::shared_ptr<detail::comm_set>();
-            if (cs && !cs->comms.empty()) {
+            auto cs = (queue.size() > 1 && !fused) ? detail::communicators(queue) : std::shared_ptr<detail::comm_set>();
+            if (fused) {
+                VEXB_CHECKED(vexb_reduce_fetch(queue[0].ordinal(), queue[0].raw(), res[0].raw(), dt, cnt, out));
+            } else if (cs && !cs->comms.empty()) {
                 std::vector<void*> bufs, streams;
                 for (unsigned d = 0; d < queue.size(); ++d) { bufs.push_back(res[d].raw()); streams.push_back(queue[d].raw()); }
                 VEXB_CHECKED(vexb_comm_allreduce(static_cast<int>(queue.size()), cs->comms.data(), bufs.data(), streams.data(), 1, dt, op));

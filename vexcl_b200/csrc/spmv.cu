@@ -557,11 +557,13 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
         const size_t stage_bytes = ((A->tile_nnz + 8) * sizeof(T) + (A->tile_nnz + 8) * 4 + (A->tile_rows + 12) * 4 + 127) & ~(size_t)127;
         size_t smem = stage_bytes * stages + 16 * stages + 16 * stages + 16;
         while (smem > 220 * 1024 && stages > 2) { --stages; smem = stage_bytes * stages + 32 * stages + 16; }
-        static int attr_set[2] = {0, 0};
+        // the opt-in shared-memory limit is a per-device function attribute: set it on every device once
+        static std::atomic<unsigned long long> attr_set[2];
         const int ti = sizeof(T) == 8 ? 0 : 1;
-        if (!attr_set[ti]) {
+        const unsigned long long bit = 1ull << (A->dev & 63);
+        if (!(attr_set[ti].load() & bit)) {
             VEXB_CUDA(cudaFuncSetAttribute(csr_pipe_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-            attr_set[ti] = 1;
+            attr_set[ti].fetch_or(bit);
         }
         int per_sm = 0;
         VEXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_pipe_kernel<T>, kPipeThreads, smem));
@@ -574,11 +576,12 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
         VEXB_LAUNCHED();
     } else if (A->fmt == VEXB_FMT_CSR) {
         const size_t smem = (A->tile_nnz + 8) * sizeof(T) + (A->tile_nnz + 8) * 4 + (A->tile_rows + 12) * 4 + 16;
-        static bool attr_set[2] = {false, false};
+        static std::atomic<unsigned long long> attr_set[2];
         const int ti = sizeof(T) == 8 ? 0 : 1;
-        if (smem > 48 * 1024 && !attr_set[ti]) {
+        const unsigned long long bit = 1ull << (A->dev & 63);
+        if (smem > 48 * 1024 && !(attr_set[ti].load() & bit)) {
             VEXB_CUDA(cudaFuncSetAttribute(csr_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set[ti] = true;
+            attr_set[ti].fetch_or(bit);
         }
         csr_stream_kernel<T><<<(unsigned)A->n_tiles, 256, smem, st>>>(A->tile, A->rowptr, A->col, (const T *)A->val, x, y, alpha, append,
                                                                      (int)A->tile_nnz, (int)A->tile_rows, A->row_ids);
