@@ -126,6 +126,9 @@ typedef enum {
     VEXB_OP_POW, VEXB_OP_ATAN2, VEXB_OP_FMOD, VEXB_OP_HYPOT,
     VEXB_OP_FMIN /* also ints: min */, VEXB_OP_FMAX /* also ints: max */,
     VEXB_OP_FMA,      /* ternary: a*b+c with one rounding (builtin fma)                 */
+    VEXB_OP_CALL,     /* user function (VEX_FUNCTION): arg = id from vexb_function_register; pops its
+                         declared number of arguments (already converted to the declared types), pushes
+                         `type` = its return type.  Expressions with calls run on the NVRTC side path. */
     VEXB_OP_COUNT_
 } vexb_opcode;
 
@@ -210,8 +213,19 @@ int vexb_partition(size_t n, int nparts, const double *weights, size_t *part);
  * ---------------------------------------------------------------------- */
 int vexb_eval(int dev, void *stream, void *lhs, int lhs_dtype, int assign_op,
               const vexb_expr *expr, size_t n, size_t index_offset);
+/* User-defined device functions (VEX_FUNCTION, vexcl/function.hpp:225): `body` is C source that refers to its
+ * arguments as prm1, prm2, ... (the reference's convention) and returns a value of `ret_dtype`.
+ * Such functions cannot be pre-compiled: an expression that calls one is turned into CUDA source
+ * (the sweep skeleton with the expression inlined), compiled once with NVRTC for sm_100a, cached, and launched
+ * through the driver API.  Setting the tunable "eval.jit" = 1 sends every non-sweep expression down the same
+ * path instead of the interpreter.  Registering the same definition twice returns the same id. */
+int vexb_function_register(const char *name, int ret_dtype, int nargs, const int *arg_dtypes,
+                           const char *body, int *id);
+/* Generated source and NVRTC build log of the kernel vexb_eval would JIT for this request (for inspection
+ * and for tests on machines without a GPU: NVRTC needs no device).  Two-call pattern on *len. */
+int vexb_jit_source(int lhs_dtype, int assign_op, const vexb_expr *expr, char *buf, size_t *len, int compile);
 /* Which kernel vexb_eval would take for this request: writes a short
- * name ("sweep:muladd", "interp", ...) to buf. */
+ * name ("sweep:muladd", "interp", "jit", ...) to buf. */
 int vexb_eval_path(int lhs_dtype, int assign_op, const vexb_expr *expr, char *buf, size_t buflen);
 
 /* ------------------------------------------------------------------------

@@ -122,8 +122,15 @@ class Reductor {
             for (unsigned d = 0; d < queue.size(); ++d) {
                 detail::ir_builder b(d);
                 expr.lower(b);
-                VEXB_CHECKED(vexb_reduce_all(queue[d].ordinal(), queue[d].raw(), &b.e, dt, p.part_size(d), p.part_start(d),
-                                             op, res[d].raw(), ws[d].raw(), fused ? ps->peers[d] : nullptr));
+                const int st = vexb_reduce_all(queue[d].ordinal(), queue[d].raw(), &b.e, dt, p.part_size(d), p.part_start(d),
+                                               op, res[d].raw(), ws[d].raw(), fused ? ps->peers[d] : nullptr);
+                if (st == VEXB_ERR_UNSUPPORTED && d == 0) {
+                    // the expression calls a user function: evaluate it into a temporary (NVRTC side path), reduce that
+                    vex::vector<typename Expr::value_type> tmp(queue, p.size);
+                    tmp = expr;
+                    return (*this)(tmp);
+                }
+                VEXB_CHECKED(st);
             }
             auto cs = (queue.size() > 1 && !fused) ? detail::communicators(queue) : std::shared_ptr<detail::comm_set>();
             if (fused) {

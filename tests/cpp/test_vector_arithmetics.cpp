@@ -87,6 +87,27 @@ BOOST_AUTO_TEST_CASE(counting_reductions)               // :113-145 (the checks 
     BOOST_CHECK_EQUAL(isum(vex::element_index(0, N)), N * (N - 1) / 2);
 }
 
+VEX_FUNCTION(size_t, greater_fn, (double, x)(double, y), return x > y;);
+VEX_FUNCTION(double, times2, (double, x), return x * 2;);
+VEX_FUNCTION_V1(sqr_v1, double(double), "return prm1 * prm1;");
+
+BOOST_AUTO_TEST_CASE(user_defined_functions)            // :113-145
+{
+    const size_t N = 1024;
+    vex::vector<double> x(ctx, N), y(ctx, N);
+    x = 1;  y = 2;
+    vex::Reductor<size_t, vex::SUM> sum(ctx);
+    BOOST_CHECK_EQUAL(sum(greater_fn(x, y)), 0u);
+    BOOST_CHECK_EQUAL(sum(greater_fn(y, x)), N);
+    vex::Reductor<double, vex::SUM> dsum(ctx);
+    BOOST_CHECK_EQUAL(dsum(times2(x)), 2.0 * N);
+    vex::vector<double> z(ctx, N);
+    z = times2(x) + sqr_v1(y) * 0.5;
+    check_sample(z, [](size_t, double a) { BOOST_CHECK_EQUAL(a, 2.0 + 4.0 * 0.5); });
+    z += times2(z) * greater_fn(y, x);
+    check_sample(z, [](size_t, double a) { BOOST_CHECK_EQUAL(a, 12.0); });
+}
+
 BOOST_AUTO_TEST_CASE(ternary_operator)                  // :238-252
 {
     const size_t n = 1024;

@@ -21,7 +21,7 @@ MAX_TERMS, MAX_CODE, MAX_STACK = 16, 64, 12
 
 _OPS = ("TERM CVT NEG LNOT ADD SUB MUL DIV MOD BAND BOR BXOR SHL SHR LT GT LE GE EQ NE LAND LOR SELECT "
         "SIN COS TAN ASIN ACOS ATAN SINH COSH TANH EXP EXP2 LOG LOG2 LOG10 SQRT RSQRT CBRT FABS FLOOR CEIL "
-        "ROUND TRUNC POW ATAN2 FMOD HYPOT FMIN FMAX FMA").split()
+        "ROUND TRUNC POW ATAN2 FMOD HYPOT FMIN FMAX FMA CALL").split()
 OP = {name: i for i, name in enumerate(_OPS)}
 
 
@@ -108,6 +108,8 @@ def lib():
         "vexb_partition": ([sz, i, P(d), P(sz)], i),
         "vexb_eval": ([i, vp, vp, i, i, P(Expr), sz, sz], i),
         "vexb_eval_path": ([i, i, P(Expr), C.c_char_p, sz], i),
+        "vexb_function_register": ([C.c_char_p, i, i, P(i), C.c_char_p, P(i)], i),
+        "vexb_jit_source": ([i, i, P(Expr), C.c_char_p, P(sz), i], i),
         "vexb_reduce_workspace_bytes": ([i, P(sz)], i),
         "vexb_reduce": ([i, vp, P(Expr), i, sz, sz, i, vp, vp], i),
         "vexb_reduce_identity": ([i, vp, i, i, vp], i),

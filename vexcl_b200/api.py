@@ -276,6 +276,34 @@ class Select(Node):
 def if_else(cond, a, b): return Select(cond, a, b)
 
 
+class Call(Node):
+    """Call of a user-defined device function (VEX_FUNCTION)."""
+    def __init__(self, fn: "UserFunction", args):
+        self.fn, self.args = fn, [wrap(a) for a in args]
+        self.dtype = fn.ret
+
+
+class UserFunction:
+    """VEX_FUNCTION(ret, name, (type, arg)..., body) (vexcl/function.hpp:225): a device function given as C source.
+    `args` is a list of (numpy dtype, name); inside `body` the arguments are available under their names (and, as in
+    the reference's older form, as prm1, prm2, ...).  Expressions that call it run on the NVRTC side path."""
+
+    def __init__(self, ret, name: str, args, body: str):
+        self.ret = _vdt(ret)
+        self.arg_types = [_vdt(t) for t, _ in args]
+        ctypes_names = {L.F64: "double", L.F32: "float", L.I32: "int", L.U32: "unsigned int", L.I64: "long long", L.U64: "unsigned long long"}
+        prologue = "".join(f"const {ctypes_names[t]} {nm} = prm{k + 1}; " for k, (t, (_, nm)) in enumerate(zip(self.arg_types, args)))
+        fid = C.c_int(-1)
+        at = (C.c_int * max(len(args), 1))(*self.arg_types)
+        L.check(L.lib().vexb_function_register(name.encode(), self.ret, len(args), at, (prologue + body).encode(), C.byref(fid)))
+        self.id, self.name = fid.value, name
+
+    def __call__(self, *args):
+        if len(args) != len(self.arg_types):
+            raise TypeError(f"{self.name} takes {len(self.arg_types)} arguments")
+        return Call(self, args)
+
+
 def _mkfunc(op):
     return lambda *args: Func(op, *args)
 
@@ -346,6 +374,10 @@ class _Lowering:
             self.lower(n.a); self.cvt(n.a.dtype, n.ctype)
             self.lower(n.b); self.cvt(n.b.dtype, n.ctype)
             self.emit(n.op, n.ctype)
+        elif isinstance(n, Call):
+            for a, t in zip(n.args, n.fn.arg_types):
+                self.lower(a); self.cvt(a.dtype, t)
+            self.emit("CALL", n.fn.ret, n.fn.id)
         elif isinstance(n, Select):
             self.lower(n.cond)
             if n.cond.dtype != L.I32:                     # any arithmetic condition: (c != 0)
@@ -356,6 +388,23 @@ class _Lowering:
             self.emit("SELECT", n.dtype)
         else:
             raise TypeError(f"cannot lower {type(n)}")
+
+
+def _has_call(n) -> bool:
+    if isinstance(n, Call):
+        return True
+    kids = [getattr(n, c, None) for c in ("a", "b", "cond")] + list(getattr(n, "args", []))
+    return any(isinstance(k, Node) and _has_call(k) for k in kids)
+
+
+def _materialize_calls(ctx, expr, n):
+    """Reductions have no run-time compiled form: an expression that calls a user function is first evaluated
+    into a temporary (one extra pass), which is then reduced by the pre-compiled kernel."""
+    if not _has_call(expr):
+        return expr
+    tmp = vector(ctx, n, _VEXB2NP[expr.dtype])
+    tmp.assign(expr)
+    return tmp
 
 
 def _find_props(n: Node):
@@ -576,6 +625,7 @@ class Reductor:
         if props is None:
             raise ValueError("expression has no vector terminal")
         n = props[1]
+        expr = _materialize_calls(ctx, expr, n)
         part = ctx.partition(n)
         cnt = 2 if self.kind == L.MINMAX else 1
         res = {}
@@ -835,6 +885,7 @@ def _reduce_device(self, expr, out: DeviceScalar):
         raise ValueError("expression has no vector terminal")
     if self.kind == L.MINMAX:
         raise ValueError("MIN_MAX needs two result slots; use the host-returning call")
+    expr = _materialize_calls(ctx, expr, props[1])
     part = ctx.partition(props[1])
     for k in ctx.local:
         ws, _ = ctx.workspace(k)

@@ -14,6 +14,8 @@
 
 namespace vexb {
 
+int jit_eval(int dev, cudaStream_t st, void *lhs, int lhs_dtype, int aop, const vexb_expr &e, size_t n, size_t index_offset);
+
 template <int SH, int AOP, class T, int U>
 __global__ void __launch_bounds__(256) sweep_kernel(T *lhs, SweepArgs a, size_t n) {
     typedef Shape<SH> S;
@@ -179,8 +181,9 @@ extern "C" int vexb_eval_path(int lhs_dtype, int assign_op, const vexb_expr *exp
     ShapeMatch m; SweepArgs a;
     // alignment is checked on the real pointers too: a 32-byte aligned dummy lhs stands in here
     alignas(32) static char dummy[32];
-    if (plan_sweep(dummy, lhs_dtype, assign_op, e, &m, &a)) snprintf(buf, buflen, "sweep:%s", shape_name(m.shape));
-    else snprintf(buf, buflen, "interp");
+    if (expr_has_call(e)) snprintf(buf, buflen, "jit");
+    else if (plan_sweep(dummy, lhs_dtype, assign_op, e, &m, &a)) snprintf(buf, buflen, "sweep:%s", shape_name(m.shape));
+    else snprintf(buf, buflen, param("eval.jit", 0) ? "jit" : "interp");
     return VEXB_OK;
 }
 
@@ -195,6 +198,9 @@ extern "C" int vexb_eval(int dev, void *stream, void *lhs, int lhs_dtype, int as
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = sm_count(dev);
+
+    // user functions have no pre-compiled form: NVRTC side path (csrc/jit.cu)
+    if (expr_has_call(e)) return jit_eval(dev, st, lhs, lhs_dtype, assign_op, e, n, index_offset);
 
     ShapeMatch m; SweepArgs a;
     if (plan_sweep(lhs, lhs_dtype, assign_op, e, &m, &a)) {
@@ -211,6 +217,8 @@ extern "C" int vexb_eval(int dev, void *stream, void *lhs, int lhs_dtype, int as
         VEXB_LAUNCHED();
         return VEXB_OK;
     }
+
+    if (param("eval.jit", 0)) return jit_eval(dev, st, lhs, lhs_dtype, assign_op, e, n, index_offset);
 
     vexb_expr prog;
     if (assign_op != VEXB_SET) { VEXB_TRY(fold_compound(e, lhs, lhs_dtype, assign_op, &prog)); }

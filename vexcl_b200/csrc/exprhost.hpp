@@ -8,6 +8,11 @@
 
 namespace vexb {
 
+// Registry of user functions (jit.cu): argument count / types of function `id`, -1 if unknown.
+int function_arity(int id);
+int function_arg_dtype(int id, int k);
+int function_ret_dtype(int id);
+
 inline int op_arity(int op) {
     if (op == VEXB_OP_TERM) return 0;
     if (op == VEXB_OP_CVT || op == VEXB_OP_NEG || op == VEXB_OP_LNOT) return 1;
@@ -67,6 +72,11 @@ inline void convert_scalar_term(vexb_term &t, int to) {
     t.dtype = (uint8_t)to;
 }
 
+inline bool expr_has_call(const vexb_expr &e) {
+    for (int pc = 0; pc < e.n_code; ++pc) if (e.code[pc].op == VEXB_OP_CALL) return true;
+    return false;
+}
+
 inline int host_result_type(const vexb_expr &e) {
     if (e.n_code <= 0) return VEXB_F64;
     const vexb_instr &in = e.code[e.n_code - 1];
@@ -96,7 +106,12 @@ inline int normalize_expr(const vexb_expr *in, vexb_expr *out, bool need_ptrs = 
     int depth = 0, maxdepth = 0;
     for (int pc = 0; pc < in->n_code; ++pc) {
         vexb_instr ins = in->code[pc];
-        const int ar = op_arity(ins.op);
+        int ar = op_arity(ins.op);
+        if (ins.op == VEXB_OP_CALL) {
+            ar = function_arity(ins.arg);
+            VEXB_CHECK(ar >= 0, "instr %d: call of unregistered function %d", pc, (int)ins.arg);
+            VEXB_CHECK(ins.type == function_ret_dtype(ins.arg), "instr %d: call result type does not match the declaration", pc);
+        }
         VEXB_CHECK(ar >= 0, "instr %d: unknown opcode %d", pc, (int)ins.op);
         VEXB_CHECK(ins.type <= VEXB_U64, "instr %d: bad type %d", pc, (int)ins.type);
         VEXB_CHECK(depth >= ar, "instr %d: stack underflow", pc);

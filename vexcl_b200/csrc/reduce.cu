@@ -306,6 +306,9 @@ extern "C" int vexb_reduce_all(int dev, void *stream, const vexb_expr *expr, int
     if (op == VEXB_SUM_KAHAN && !dtype_is_float(dtype)) op = VEXB_SUM;
     vexb_expr e;
     VEXB_TRY(normalize_expr(expr, &e, n != 0));
+    if (expr_has_call(e))
+        VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "reductions of expressions that call user functions are evaluated into a temporary first "
+                                        "(the front ends do this); vexb_reduce itself has no run-time compiled form");
     if (n == 0) {                                                               // reductor.hpp:318-321
         VEXB_TRY(vexb_reduce_identity(dev, stream, dtype, op, d_result));
         return pa.nranks > 1 ? vexb_peer_allreduce(peer, stream, d_result, dtype, op) : VEXB_OK;
