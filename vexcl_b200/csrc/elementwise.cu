@@ -14,7 +14,8 @@
 
 namespace vexb {
 
-int jit_eval(int dev, cudaStream_t st, void *lhs, int lhs_dtype, int aop, const vexb_expr &e, size_t n, size_t index_offset);
+int jit_eval(int dev, cudaStream_t st, void *lhs, int lhs_dtype, int aop, const vexb_expr &e, size_t n, size_t index_offset,
+             int mode, bool *done);
 
 template <int SH, int AOP, class T, int U>
 __global__ void __launch_bounds__(256) sweep_kernel(T *lhs, SweepArgs a, size_t n) {
@@ -183,7 +184,7 @@ extern "C" int vexb_eval_path(int lhs_dtype, int assign_op, const vexb_expr *exp
     alignas(32) static char dummy[32];
     if (expr_has_call(e)) snprintf(buf, buflen, "jit");
     else if (plan_sweep(dummy, lhs_dtype, assign_op, e, &m, &a)) snprintf(buf, buflen, "sweep:%s", shape_name(m.shape));
-    else snprintf(buf, buflen, param("eval.jit", 0) ? "jit" : "interp");
+    else snprintf(buf, buflen, param("eval.jit", 0) == 1 ? "jit" : "interp");
     return VEXB_OK;
 }
 
@@ -200,7 +201,7 @@ extern "C" int vexb_eval(int dev, void *stream, void *lhs, int lhs_dtype, int as
     const int sms = sm_count(dev);
 
     // user functions have no pre-compiled form: NVRTC side path (csrc/jit.cu)
-    if (expr_has_call(e)) return jit_eval(dev, st, lhs, lhs_dtype, assign_op, e, n, index_offset);
+    if (expr_has_call(e)) { bool done = false; return jit_eval(dev, st, lhs, lhs_dtype, assign_op, e, n, index_offset, 1, &done); }
 
     ShapeMatch m; SweepArgs a;
     if (plan_sweep(lhs, lhs_dtype, assign_op, e, &m, &a)) {
@@ -218,7 +219,14 @@ extern "C" int vexb_eval(int dev, void *stream, void *lhs, int lhs_dtype, int as
         return VEXB_OK;
     }
 
-    if (param("eval.jit", 0)) return jit_eval(dev, st, lhs, lhs_dtype, assign_op, e, n, index_offset);
+    // No hand-written sweep for this shape.  eval.jit: 0 = always the interpreter, 1 = always the NVRTC-specialised
+    // kernel, 2 (default) = interpreter for the first uses of a shape, specialised kernel once it is hot.
+    const long jit_mode = param("eval.force_interp", 0) ? param("eval.jit", 0) : param("eval.jit", 2);
+    if (jit_mode) {
+        bool done = false;
+        VEXB_TRY(jit_eval(dev, st, lhs, lhs_dtype, assign_op, e, n, index_offset, (int)jit_mode, &done));
+        if (done) return VEXB_OK;
+    }
 
     vexb_expr prog;
     if (assign_op != VEXB_SET) { VEXB_TRY(fold_compound(e, lhs, lhs_dtype, assign_op, &prog)); }
