@@ -128,13 +128,20 @@ class Context:
         self.peers = None
         if nranks > 1 and use_peer:
             # peer-memory group: exchange the CUDA IPC handles of the mailboxes through the launcher's all-gather
+            # Every rank runs both collectives whatever happens locally, and the group is used only if ALL ranks
+            # succeeded -- otherwise everybody falls back to ncclAllReduce (no rank may wait on a missing peer).
             p = C.c_void_p()
             h = C.create_string_buffer(64)
-            L.check(lib.vexb_peer_create(dev, rank, nranks, C.byref(p), h))
+            ok = lib.vexb_peer_create(dev, rank, nranks, C.byref(p), h) == L.OK
             allh = allgather(np.frombuffer(h.raw, dtype=np.uint8).copy())
-            cat = b"".join(np.asarray(a, dtype=np.uint8).tobytes() for a in allh)
-            L.check(lib.vexb_peer_connect(p, C.create_string_buffer(cat, 64 * nranks)))
-            self.peers = {rank: p}
+            if ok:
+                cat = b"".join(np.asarray(a, dtype=np.uint8).tobytes() for a in allh)
+                ok = lib.vexb_peer_connect(p, C.create_string_buffer(cat, 64 * nranks)) == L.OK
+            everybody = allgather(np.array([1 if ok else 0], dtype=np.int64))
+            if all(int(np.asarray(a)[0]) == 1 for a in everybody):
+                self.peers = {rank: p}
+            elif p.value:
+                lib.vexb_peer_destroy(p)
         self._ws = {}
         return self
 
