@@ -391,6 +391,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             extra.update(bench_vectors(ctx, vx, args, peak))
         except vx.VexbError as e:
             extra["error"] = str(e)
+        try:
+            extra["ccsr_spmv"] = bench_ccsr(ctx, vx, args, peak)
+        except vx.VexbError as e:
+            extra["ccsr_spmv"] = {"error": str(e)}
         if not args.no_cpu_baseline:
             cpu_base, y_cpu = cpu_baseline_sample()
             import oracle                      # checker only: parity of the timed kernel on the oracle's x
@@ -471,6 +475,34 @@ def bench_cg(ctx, vx, rank, world, args, barrier, max_over_ranks, peak):
                 "convention": "unfused reference-equivalent traffic: SpMV + dot 16N + axpy 24N + axpy 24N + dot 8N + p-update 24N",
                 "residual2_after": cg.residual2()})
     return out
+
+
+def bench_ccsr(ctx, vx, args, peak):
+    """examples/benchmark.cpp:481-606: y += A*x with vex::SpMatCCSR on the 3-D Poisson matrix; n = 256 here (the
+    reference uses 128, whose 50 MB working set would sit in the 126 MB L2)."""
+    from vexcl_b200 import gen
+    n = 256
+    N = n ** 3
+    idx, row, col, val = gen.poisson_ccsr(n)
+    A = vx.SpMatCCSR(ctx, N, idx, row, col, val)
+    x, y = vx.vector(ctx, N), vx.vector(ctx, N)
+    x.assign(vx.ElementIndex() * (1.0 / N) + 0.5)
+    y.assign(0.0)
+    steps = max(10, min(args.steps, 40))
+    variants = {}
+    for kernel in (1, 2, 3):                                  # csrc/ccsr.cu: ccsr.kernel tunable
+        vx.set_param("ccsr.kernel", kernel)
+        variants[f"kernel{kernel}_ms"] = time_loop(ctx, lambda: A.apply(x, y, 1.0, True), steps, 3, ctx.finish) / steps
+    vx.set_param("ccsr.kernel", 0)                            # the library default is what is reported
+    ms = time_loop(ctx, lambda: A.apply(x, y, 1.0, True), steps, 3, ctx.finish)
+    _, nnz = gen.poisson_nnz(3, n)
+    t = ms * 1e-3 / steps
+    compulsory = N * (A.info().idx_bytes + 24)               # idx as stored on the device + x + y read + y written
+    return {"grid": n, "rows": N, "ms": ms / steps, "rows_per_s": N / t, "variants": variants,
+            "gbs_compulsory": compulsory / t / 1e9, "frac_of_peak": compulsory / t / 1e9 / peak,
+            "gbs_by_reference_formula": (nnz * 20 + 4 * N * 8) / t / 1e9,
+            "note": "y += A*x; compulsory bytes = (1-byte idx + x + y in + y out) per row; the reference's own figure "
+                    "(benchmark.cpp:563) counts the matrix as if it were CSR"}
 
 
 def bench_vectors(ctx, vx, args, peak):

@@ -366,6 +366,28 @@ int vexb_spmat_hell_download(const vexb_spmat *A, int32_t *ell_col, void *ell_va
 int vexb_spmv(int dev, void *stream, const vexb_spmat *A, const void *x, void *y, double alpha, int append);
 
 /* ------------------------------------------------------------------------
+ * Compressed CSR for stencil-like matrices: vex::SpMatCCSR
+ * (vexcl/spmat/ccsr.hpp:54-86 ctor, :176-201 kernel).  Single device.
+ *   y[i] (=|+=) alpha * sum_{j = row[idx[i]] .. row[idx[i]+1]} val[j] * x[i + col[j]]
+ * idx: n entries naming one of the m unique rows; row: m+1 offsets; col: SIGNED
+ * offsets from the diagonal.  Unlike the reference, create() rejects a matrix
+ * whose rows reach outside [0, n).
+ * ---------------------------------------------------------------------- */
+typedef struct vexb_ccsr vexb_ccsr;
+typedef struct {
+    size_t  nrows, unique_rows, nnz;
+    int32_t idx_bytes;       /* width idx was re-encoded to on the device (1, 2 or 4) */
+    int32_t table_in_smem;   /* unique-row table staged in shared memory by the kernel */
+    size_t  device_bytes;
+} vexb_ccsr_info;
+int vexb_ccsr_create(int dev, void *stream, size_t n, size_t m, const void *idx, int idx_bytes,
+                     const void *row, int row_bytes, const void *col, int col_bytes,
+                     const void *val, int val_dtype, vexb_ccsr **out);
+int vexb_ccsr_destroy(vexb_ccsr *A);
+int vexb_ccsr_get_info(const vexb_ccsr *A, vexb_ccsr_info *info);
+int vexb_ccsr_spmv(int dev, void *stream, const vexb_ccsr *A, const void *x, void *y, double alpha, int append);
+
+/* ------------------------------------------------------------------------
  * Distributed SpMat part: the slice of a vex::SpMat owned by one device
  * (spmat.hpp:71-106 ctor body for one d, :120-185 apply).
  * `col` holds GLOBAL column ids for the strip's rows, indexed by ptr values

@@ -21,6 +21,7 @@ struct function_node : vector_expr_tag {
     typedef typename std::common_type<typename detail::value_of<Args>::type...>::type common;
     typedef typename std::conditional<FloatOnly && std::is_integral<common>::value, double,
                                       typename detail::promoted<common>::type>::type value_type;
+    static const size_t multi_size = detail::max_ncomp<Args...>::value;
     std::tuple<Args...> args;
     explicit function_node(Args... a) : args(a...) {}
 
@@ -41,12 +42,12 @@ struct function_node : vector_expr_tag {
 
 #define VEXCL_BUILTIN_1(name, OP, FLOATONLY) \
     template <class A> \
-    typename std::enable_if<is_vector_expr<A>::value, function_node<OP, FLOATONLY, typename detail::operand<A>::type> >::type \
+    const typename std::enable_if<is_vector_expr<A>::value, function_node<OP, FLOATONLY, typename detail::operand<A>::type> >::type \
     name(const A &a) { return function_node<OP, FLOATONLY, typename detail::operand<A>::type>(detail::operand<A>::wrap(a)); }
 
 #define VEXCL_BUILTIN_2(name, OP, FLOATONLY) \
     template <class A, class B> \
-    typename std::enable_if<detail::is_operand<A>::value && detail::is_operand<B>::value && \
+    const typename std::enable_if<detail::is_operand<A>::value && detail::is_operand<B>::value && \
                             (is_vector_expr<A>::value || is_vector_expr<B>::value), \
         function_node<OP, FLOATONLY, typename detail::operand<A>::type, typename detail::operand<B>::type> >::type \
     name(const A &a, const B &b) { \
@@ -55,7 +56,7 @@ struct function_node : vector_expr_tag {
 
 #define VEXCL_BUILTIN_3(name, OP, FLOATONLY) \
     template <class A, class B, class C> \
-    typename std::enable_if<detail::is_operand<A>::value && detail::is_operand<B>::value && detail::is_operand<C>::value && \
+    const typename std::enable_if<detail::is_operand<A>::value && detail::is_operand<B>::value && detail::is_operand<C>::value && \
                             (is_vector_expr<A>::value || is_vector_expr<B>::value || is_vector_expr<C>::value), \
         function_node<OP, FLOATONLY, typename detail::operand<A>::type, typename detail::operand<B>::type, typename detail::operand<C>::type> >::type \
     name(const A &a, const B &b, const C &c) { \
@@ -123,6 +124,7 @@ template <class Ret, class... Args>
 struct call_node : vector_expr_tag {
     VEXCL_NODE_COMMON
     typedef typename detail::promoted<Ret>::type value_type;
+    static const size_t multi_size = detail::max_ncomp<Args...>::value;
     int id; std::vector<int> arg_types;
     std::tuple<Args...> args;
     call_node(int id, const std::vector<int> &arg_types, Args... a) : id(id), arg_types(arg_types), args(a...) {}
@@ -159,7 +161,7 @@ struct user_function {
         return fid;
     }
     template <class... A>
-    call_node<Ret, typename detail::operand<A>::type...> operator()(const A&... a) const {
+    const call_node<Ret, typename detail::operand<A>::type...> operator()(const A&... a) const {
         std::vector<int> types;
         const int fid = id(&types);
         precondition(types.size() == sizeof...(A), std::string(Impl::fn_name()) + ": wrong number of arguments");

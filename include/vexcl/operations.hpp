@@ -47,7 +47,8 @@ namespace detail {
 struct ir_builder {
     vexb_expr e;
     unsigned part;
-    explicit ir_builder(unsigned part) : part(part) { std::memset(&e, 0, sizeof(e)); }
+    int comp;                       ///< component being lowered when the expression is a multi-expression, else -1
+    explicit ir_builder(unsigned part, int comp = -1) : part(part), comp(comp) { std::memset(&e, 0, sizeof(e)); }
 
     int new_term() {
         precondition(e.n_terms < VEXB_MAX_TERMS, "expression has too many terminals");
@@ -87,6 +88,7 @@ struct expr_props {
     std::vector<size_t> part;
     size_t size = 0;
     bool sized = false;
+    int comp = -1;                  ///< component being prepared (multi-expressions), else -1
 
     void see(const std::vector<backend::command_queue> &q, const std::vector<size_t> &p, size_t n) {
         if (!queue) { queue = &q; part = p; }
@@ -144,6 +146,14 @@ template <class X> struct is_operand
 
 template <class X> struct value_of { typedef typename std::decay<X>::type::value_type type; };
 
+// Number of components of a multi-expression (multivector.hpp); 0 for ordinary vector expressions.
+template <class X, class Enable = void> struct ncomp : std::integral_constant<size_t, 0> {};
+template <class X> struct ncomp<X, typename std::enable_if<(std::decay<X>::type::multi_size > 0)>::type>
+    : std::integral_constant<size_t, std::decay<X>::type::multi_size> {};
+template <class... X> struct max_ncomp : std::integral_constant<size_t, 0> {};
+template <class X, class... Y> struct max_ncomp<X, Y...>
+    : std::integral_constant<size_t, (ncomp<X>::value > max_ncomp<Y...>::value ? ncomp<X>::value : max_ncomp<Y...>::value)> {};
+
 } // namespace detail
 
 #define VEXCL_NODE_COMMON static const bool hold_by_reference = false;
@@ -176,6 +186,8 @@ struct binary_node : vector_expr_tag {
     typedef typename detail::promoted<raw_value>::type value_type;
     typedef typename std::common_type<lhs_value, rhs_value>::type operand_type;   // type the operands meet in
 
+    static const size_t multi_size = detail::max_ncomp<L, R>::value;
+
     L l; R r;
     binary_node(L l, R r) : l(l), r(r) {}
 
@@ -199,6 +211,7 @@ struct unary_node : vector_expr_tag {
     VEXCL_NODE_COMMON
     typedef typename detail::value_of<A>::type arg_value;
     typedef typename std::conditional<std::is_same<Tag, op::logical_not>::value, int, arg_value>::type value_type;
+    static const size_t multi_size = detail::ncomp<A>::value;
     A a;
     explicit unary_node(A a) : a(a) {}
     int lower(detail::ir_builder &b) const {
@@ -215,6 +228,7 @@ struct select_node : vector_expr_tag {
     VEXCL_NODE_COMMON
     typedef typename detail::promoted<typename std::common_type<typename detail::value_of<A>::type,
                                                                  typename detail::value_of<B>::type>::type>::type value_type;
+    static const size_t multi_size = detail::max_ncomp<C, A, B>::value;
     C c; A a; B b_;
     select_node(C c, A a, B b) : c(c), a(a), b_(b) {}
     int lower(detail::ir_builder &b) const {
@@ -235,7 +249,7 @@ struct select_node : vector_expr_tag {
 };
 
 template <class C, class A, class B>
-typename std::enable_if<detail::is_operand<C>::value && detail::is_operand<A>::value && detail::is_operand<B>::value &&
+const typename std::enable_if<detail::is_operand<C>::value && detail::is_operand<A>::value && detail::is_operand<B>::value &&
                         (is_vector_expr<C>::value || is_vector_expr<A>::value || is_vector_expr<B>::value),
     select_node<typename detail::operand<C>::type, typename detail::operand<A>::type, typename detail::operand<B>::type> >::type
 if_else(const C &c, const A &a, const B &b) {
@@ -246,7 +260,7 @@ if_else(const C &c, const A &a, const B &b) {
 // ---- operators -------------------------------------------------------------------------------
 #define VEXCL_BINARY_OPERATOR(sym, tag) \
     template <class L, class R> \
-    typename std::enable_if<detail::is_operand<L>::value && detail::is_operand<R>::value && \
+    const typename std::enable_if<detail::is_operand<L>::value && detail::is_operand<R>::value && \
                             (is_vector_expr<L>::value || is_vector_expr<R>::value), \
         binary_node<op::tag, typename detail::operand<L>::type, typename detail::operand<R>::type> >::type \
     operator sym(const L &l, const R &r) { \
@@ -263,11 +277,11 @@ VEXCL_BINARY_OPERATOR(&&, logical_and) VEXCL_BINARY_OPERATOR(||, logical_or)
 #undef VEXCL_BINARY_OPERATOR
 
 template <class A>
-typename std::enable_if<is_vector_expr<A>::value, unary_node<op::negate, typename detail::operand<A>::type> >::type
+const typename std::enable_if<is_vector_expr<A>::value, unary_node<op::negate, typename detail::operand<A>::type> >::type
 operator-(const A &a) { return unary_node<op::negate, typename detail::operand<A>::type>(detail::operand<A>::wrap(a)); }
 
 template <class A>
-typename std::enable_if<is_vector_expr<A>::value, unary_node<op::logical_not, typename detail::operand<A>::type> >::type
+const typename std::enable_if<is_vector_expr<A>::value, unary_node<op::logical_not, typename detail::operand<A>::type> >::type
 operator!(const A &a) { return unary_node<op::logical_not, typename detail::operand<A>::type>(detail::operand<A>::wrap(a)); }
 
 template <class A>
@@ -385,13 +399,14 @@ namespace detail {
 
 /// lhs OP= expr on every device slice (replaces assign_expression, operations.hpp:1818-1897).
 template <class OP, class T, class Expr>
-void assign_expression(vex::vector<T> &lhs, const Expr &expr) {
+void assign_expression(vex::vector<T> &lhs, const Expr &expr, int comp = -1) {
     expr_props p;
+    p.comp = comp;
     p.see(lhs.queue_list(), lhs.partition(), lhs.size());
     expr.props(p);
     const std::vector<backend::command_queue> &queue = lhs.queue_list();
     for (unsigned d = 0; d < queue.size(); ++d) {
-        ir_builder b(d);
+        ir_builder b(d, comp);
         expr.lower(b);
         VEXB_CHECKED(vexb_eval(queue[d].ordinal(), queue[d].raw(), lhs(d).raw(), dtype_of<T>::value, OP::op,
                                &b.e, lhs.part_size(d), lhs.part_start(d)));

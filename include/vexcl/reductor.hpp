@@ -106,9 +106,23 @@ class Reductor {
         }
 
         template <class Expr>
-        typename std::enable_if<is_vector_expr<Expr>::value, result_type>::type
+        typename std::enable_if<is_vector_expr<Expr>::value && detail::ncomp<Expr>::value == 0, result_type>::type
+        operator()(const Expr &expr) const { return reduce(expr, -1); }
+
+        /// Multi-expressions reduce component by component (reductor.hpp:341-349).
+        template <class Expr>
+        typename std::enable_if<is_vector_expr<Expr>::value && (detail::ncomp<Expr>::value > 0),
+                                std::array<result_type, detail::ncomp<Expr>::value> >::type
         operator()(const Expr &expr) const {
+            std::array<result_type, detail::ncomp<Expr>::value> r;
+            for (size_t i = 0; i < r.size(); ++i) r[i] = reduce(expr, static_cast<int>(i));
+            return r;
+        }
+    private:
+        template <class Expr>
+        result_type reduce(const Expr &expr, int comp) const {
             detail::expr_props p;
+            p.comp = comp;
             expr.props(p);
             const int op = RDC::op, dt = dtype_of<ScalarType>::value;
             const int cnt = op == VEXB_MINMAX ? 2 : 1;
@@ -120,15 +134,15 @@ class Reductor {
             auto ps = queue.size() > 1 ? detail::peer_group(queue) : std::shared_ptr<detail::peer_set>();
             const bool fused = ps && !ps->peers.empty();
             for (unsigned d = 0; d < queue.size(); ++d) {
-                detail::ir_builder b(d);
+                detail::ir_builder b(d, comp);
                 expr.lower(b);
                 const int st = vexb_reduce_all(queue[d].ordinal(), queue[d].raw(), &b.e, dt, p.part_size(d), p.part_start(d),
                                                op, res[d].raw(), ws[d].raw(), fused ? ps->peers[d] : nullptr);
                 if (st == VEXB_ERR_UNSUPPORTED && d == 0) {
                     // the expression calls a user function: evaluate it into a temporary (NVRTC side path), reduce that
                     vex::vector<typename Expr::value_type> tmp(queue, p.size);
-                    tmp = expr;
-                    return (*this)(tmp);
+                    detail::assign_expression<assign::SET>(tmp, expr, comp);
+                    return reduce(tmp, -1);
                 }
                 VEXB_CHECKED(st);
             }
@@ -150,7 +164,6 @@ class Reductor {
             }
             return detail::reduce_result<ScalarType, RDC>::make(out);
         }
-    private:
         std::vector<backend::command_queue> queue;
         mutable std::vector<backend::device_vector<char>> ws;
         mutable std::vector<backend::device_vector<ScalarType>> res;

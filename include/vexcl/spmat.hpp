@@ -14,6 +14,7 @@
 #include <memory>
 #include "reductor.hpp"
 #include "vector.hpp"
+#include "multivector.hpp"
 
 namespace vex {
 
@@ -100,6 +101,64 @@ template <typename val_t, typename col_t, typename idx_t>
 additive_operator<SpMat<val_t, col_t, idx_t>, vector<val_t>>
 operator*(const SpMat<val_t, col_t, idx_t> &A, const vector<val_t> &x) {
     return additive_operator<SpMat<val_t, col_t, idx_t>, vector<val_t>>(A, x);
+}
+
+/// `A * x` as a terminal of any vector expression (vexcl/spmat/inline_spmv.hpp:42-76), e.g.
+///     eps = sum(fabs(f - vex::make_inline(A * x)));
+/// The reference restricts this to one device because it inlines the row loop into the consumer's kernel; here the
+/// product is evaluated by the SpMV kernels into a temporary when the enclosing expression is launched, so it also
+/// works across devices.
+template <class M, class V>
+struct inline_spmv : vector_expr_tag {
+    static const bool hold_by_reference = false;
+    typedef typename V::value_type value_type;
+    const M &A; const V &x;
+    mutable std::shared_ptr<vex::vector<value_type>> y;
+    inline_spmv(const M &A, const V &x) : A(A), x(x) {}
+    void props(detail::expr_props &p) const {
+        if (!y || y->size() != A.rows()) y = std::make_shared<vex::vector<value_type>>(x.queue_list(), A.rows());
+        A.apply(x, *y, 1, false);
+        y->props(p);
+    }
+    int lower(detail::ir_builder &b) const { return y->lower(b); }
+};
+
+template <typename val_t, typename col_t, typename idx_t>
+const inline_spmv<SpMat<val_t, col_t, idx_t>, vector<val_t>>
+make_inline(const additive_operator<SpMat<val_t, col_t, idx_t>, vector<val_t>> &base) {
+    precondition(base.scale == 1, "make_inline: scale the inlined product inside the expression instead");
+    return inline_spmv<SpMat<val_t, col_t, idx_t>, vector<val_t>>(base.A, base.x);
+}
+
+// ---- multivectors: one product per component (spmat.hpp:188-196, inline_spmv.hpp:78-106) ----------------------------
+template <typename val_t, typename col_t, typename idx_t, size_t N>
+additive_operator<SpMat<val_t, col_t, idx_t>, multivector<val_t, N>>
+operator*(const SpMat<val_t, col_t, idx_t> &A, const multivector<val_t, N> &x) {
+    return additive_operator<SpMat<val_t, col_t, idx_t>, multivector<val_t, N>>(A, x);
+}
+
+template <class M, class T, size_t N>
+struct inline_multi_spmv : vector_expr_tag {
+    static const bool hold_by_reference = false;
+    static const size_t multi_size = N;
+    typedef T value_type;
+    const M &A; const multivector<T, N> &x;
+    mutable std::shared_ptr<multivector<T, N>> y;
+    inline_multi_spmv(const M &A, const multivector<T, N> &x) : A(A), x(x) {}
+    void props(detail::expr_props &p) const {
+        precondition(p.comp >= 0 && static_cast<size_t>(p.comp) < N, "inlined multivector product used in a single-vector expression");
+        if (!y || y->size() != A.rows()) y = std::make_shared<multivector<T, N>>(x.queue_list(), A.rows());
+        A.apply(x(p.comp), (*y)(p.comp), 1, false);
+        (*y)(p.comp).props(p);
+    }
+    int lower(detail::ir_builder &b) const { return y->lower(b); }
+};
+
+template <typename val_t, typename col_t, typename idx_t, size_t N>
+const inline_multi_spmv<SpMat<val_t, col_t, idx_t>, val_t, N>
+make_inline(const additive_operator<SpMat<val_t, col_t, idx_t>, multivector<val_t, N>> &base) {
+    precondition(base.scale == 1, "make_inline: scale the inlined product inside the expression instead");
+    return inline_multi_spmv<SpMat<val_t, col_t, idx_t>, val_t, N>(base.A, base.x);
 }
 
 } // namespace vex

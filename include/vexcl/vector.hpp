@@ -187,6 +187,8 @@ class vector : public vector_expr_tag {
         template <class Expr> \
         typename std::enable_if<detail::is_operand<Expr>::value, const vector&>::type \
         operator cop(const Expr &expr) { \
+            static_assert(detail::ncomp<typename detail::operand<Expr>::type>::value == 0, \
+                          "a multi-expression can only be assigned to a multivector or vex::tie(...)"); \
             detail::assign_expression<assign::tag>(*this, detail::operand<Expr>::wrap(expr)); \
             return *this; \
         }

@@ -9,11 +9,13 @@
 #include "profiler.hpp"
 #include "operations.hpp"
 #include "vector.hpp"
+#include "multivector.hpp"
 #include "function.hpp"
 #include "element_index.hpp"
 #include "tagged_terminal.hpp"
 #include "reductor.hpp"
 #include "spmat.hpp"
+#include "spmat/ccsr.hpp"
 #include "sparse/product.hpp"
 #include "sparse/matrix.hpp"
 #include "sparse/distributed.hpp"

@@ -70,6 +70,24 @@ BOOST_AUTO_TEST_CASE(empty_rows)
     BOOST_CHECK_EQUAL(Y[n - 1], 0.0);
 }
 
+BOOST_AUTO_TEST_CASE(inline_spmv)                         // tests/spmv.cpp:233-260
+{
+    const size_t n = 1024;
+    std::vector<vex::command_queue> queue(1, ctx.queue(0));
+    std::vector<size_t> row, col; std::vector<double> val;
+    random_matrix(n, n, 16, row, col, val);
+    std::vector<double> x = random_vector<double>(n);
+    vex::SpMat<double> A(queue, n, n, row.data(), col.data(), val.data());
+    vex::vector<double> X(queue, x), Y(queue, n);
+    Y = sin(vex::make_inline(A * X));
+    check_sample(Y, [&](size_t idx, double a) { BOOST_CHECK_CLOSE(a, sin(row_sum(row, col, val, x, idx)), 1e-8); });
+    vex::Reductor<double, vex::MAX> max(queue);
+    std::vector<double> y(n);
+    for (size_t i = 0; i < n; ++i) y[i] = row_sum(row, col, val, x, i);
+    vex::vector<double> F(queue, y);
+    BOOST_CHECK_SMALL(max(fabs(F - vex::make_inline(A * X))), 1e-10);
+}
+
 BOOST_AUTO_TEST_CASE(poisson_benchmark_matrix)          // examples/benchmark.cpp:357-473 at n = 32
 {
     const size_t n = 32, N = n * n * n;

@@ -12,7 +12,7 @@ BIN = Path(__file__).resolve().parent / "cpp" / "bin"
 
 
 @pytest.mark.parametrize("parts", ["2", "1"])
-@pytest.mark.parametrize("name", ["test_vector_arithmetics", "test_spmv", "test_sparse_matrices"])
+@pytest.mark.parametrize("name", ["test_vector_arithmetics", "test_spmv", "test_sparse_matrices", "test_multivector"])
 def test_cpp_front_end(built, name, parts):
     from vexcl_b200 import build
     build.build_cpp_tests()

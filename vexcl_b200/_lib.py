@@ -55,6 +55,11 @@ class SpmatInfo(C.Structure):
                 ("device_bytes", C.c_size_t)]
 
 
+class CcsrInfo(C.Structure):
+    _fields_ = [("nrows", C.c_size_t), ("unique_rows", C.c_size_t), ("nnz", C.c_size_t), ("idx_bytes", C.c_int32),
+                ("table_in_smem", C.c_int32), ("device_bytes", C.c_size_t)]
+
+
 class DspmatInfo(C.Structure):
     _fields_ = [("nrows", C.c_size_t), ("ncols_local", C.c_size_t), ("n_ghost", C.c_size_t), ("n_send", C.c_size_t),
                 ("loc_nnz", C.c_size_t), ("rem_nnz", C.c_size_t), ("loc", SpmatInfo), ("rem", SpmatInfo)]
@@ -141,6 +146,10 @@ def lib():
         "vexb_spmat_get_info": ([vp, P(SpmatInfo)], i),
         "vexb_spmat_hell_download": ([vp, vp, vp, vp, vp, vp], i),
         "vexb_spmv": ([i, vp, vp, vp, vp, d, i], i),
+        "vexb_ccsr_create": ([i, vp, sz, sz, vp, i, vp, i, vp, i, vp, i, P(vp)], i),
+        "vexb_ccsr_destroy": ([vp], i),
+        "vexb_ccsr_get_info": ([vp, P(CcsrInfo)], i),
+        "vexb_ccsr_spmv": ([i, vp, vp, vp, vp, d, i], i),
         "vexb_dspmat_create": ([i, vp, i, vp, sz, vp, i, vp, i, vp, i, i, P(vp)], i),
         "vexb_dspmat_destroy": ([vp], i),
         "vexb_dspmat_get_info": ([vp, P(DspmatInfo)], i),

@@ -775,6 +775,55 @@ class SpMat:
         return y
 
 
+class SpMatCCSR:
+    """vex::SpMatCCSR<val_t, col_t, idx_t> (spmat/ccsr.hpp:54-86): unique rows with diagonal-relative columns.
+    Single device, like the reference: the context must have one slot."""
+
+    def __init__(self, ctx: Context, n: int, idx, row, col, val):
+        if ctx.nparts != 1:
+            raise ValueError("SpMatCCSR does not support multi-device contexts (ccsr.hpp:49-52)")
+        self.ctx, self.n = ctx, int(n)
+        idx, row = np.ascontiguousarray(idx), np.ascontiguousarray(row)
+        col, val = np.ascontiguousarray(col), np.ascontiguousarray(val)
+        if idx.dtype.itemsize not in (4, 8) or row.dtype.itemsize not in (4, 8) or col.dtype.itemsize not in (4, 8):
+            raise TypeError("idx/row/col must be 32- or 64-bit integers")
+        if col.dtype.kind != "i":
+            raise TypeError("Column type for CCSR format has to be signed.")           # ccsr.hpp:56-57
+        self.m = row.size - 1
+        self.val_dtype = _vdt(val.dtype)
+        self.h = C.c_void_p()
+        k = ctx.local[0]
+        L.check(L.lib().vexb_ccsr_create(ctx.devs[k], ctx.streams[k], self.n, self.m, _ip(idx), idx.dtype.itemsize,
+                                         _ip(row), row.dtype.itemsize, _ip(col), col.dtype.itemsize, _ip(val),
+                                         self.val_dtype, C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            L.lib().vexb_ccsr_destroy(self.h)
+        except Exception:
+            pass
+
+    def rows(self): return self.n
+    def cols(self): return self.n
+
+    def info(self) -> L.CcsrInfo:
+        info = L.CcsrInfo()
+        L.check(L.lib().vexb_ccsr_get_info(self.h, C.byref(info)))
+        return info
+
+    def __mul__(self, x):
+        if not isinstance(x, vector):
+            return NotImplemented
+        return SpMVTerm(self, x)
+
+    def apply(self, x: vector, y: vector, alpha: float = 1.0, append: bool = False):
+        if x.n != self.n or y.n != self.n:
+            raise ValueError("SpMatCCSR::apply: vector sizes do not match the matrix")
+        k = self.ctx.local[0]
+        L.check(L.lib().vexb_ccsr_spmv(self.ctx.devs[k], self.ctx.streams[k], self.h, x.bufs[k], y.bufs[k], float(alpha), int(append)))
+        return y
+
+
 # ------------------------------------------------------------------------------------------- helpers for timing / host staging
 class PinnedArray:
     """Page-locked host buffer exposed as a numpy array (.a)."""

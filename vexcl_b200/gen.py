@@ -60,6 +60,27 @@ def poisson_strip(dim: int, nx: int, ny: int | None = None, nz: int | None = Non
     return row.astype(index_dtype), col.astype(index_dtype), val
 
 
+def poisson_ccsr(n: int, index_dtype=np.uint64, col_dtype=np.int32):
+    """The 3-D Poisson matrix on an n^3 grid in CCSR form, as the reference builds it (examples/benchmark.cpp:493-545,
+    tests/spmv.cpp:150-197): unique row 0 = boundary (identity), unique row 1 = 7-point stencil.
+    Returns (idx, row, col, val)."""
+    h2i = float((n - 1) * (n - 1))
+    row = np.array([0, 1, 8], dtype=index_dtype)
+    col = np.array([0, -n * n, -n, -1, 0, 1, n, n * n], dtype=col_dtype)
+    val = np.array([1.0, -h2i, -h2i, -h2i, 6 * h2i, -h2i, -h2i, -h2i])
+    g = np.arange(n)
+    edge = (g == 0) | (g == n - 1)
+    bnd = edge[:, None, None] | edge[None, :, None] | edge[None, None, :]
+    idx = np.where(bnd, 0, 1).astype(index_dtype).ravel()
+    return idx, row, col, val
+
+
+def ccsr_bytes(nrows: int, idx_bytes: int = 8) -> int:
+    """Algorithmic bytes of y = A*x for a CCSR matrix: idx as the reference stores it (size_t), x and y once; the
+    unique-row table is negligible."""
+    return nrows * (idx_bytes + 16)
+
+
 def poisson_nnz(dim: int, nx: int, ny: int | None = None, nz: int | None = None) -> tuple[int, int]:
     nx, ny, nz = poisson_dims(dim, nx, ny, nz)
     N = nx * ny * nz
