@@ -490,10 +490,13 @@ def bench_ccsr(ctx, vx, args, peak):
     y.assign(0.0)
     steps = max(10, min(args.steps, 40))
     variants = {}
-    for kernel in (1, 2, 3):                                  # csrc/ccsr.cu: ccsr.kernel tunable
-        vx.set_param("ccsr.kernel", kernel)
-        variants[f"kernel{kernel}_ms"] = time_loop(ctx, lambda: A.apply(x, y, 1.0, True), steps, 3, ctx.finish) / steps
-    vx.set_param("ccsr.kernel", 0)                            # the library default is what is reported
+    for name, prm in (("no_hoist", ("ccsr.hoist", 0)), ("table_from_global", ("ccsr.smem", 0)),
+                      ("two_rows_per_thread", ("ccsr.kernel", 3))):         # csrc/ccsr.cu tunables, for the record
+        vx.set_param(prm[0], prm[1])
+        variants[name + "_ms"] = time_loop(ctx, lambda: A.apply(x, y, 1.0, True), steps, 3, ctx.finish) / steps
+        vx.set_param(prm[0], 1 if prm[0] != "ccsr.kernel" else 0)
+    variants["y=A*x_ms"] = time_loop(ctx, lambda: A.apply(x, y, 1.0, False), steps, 3, ctx.finish) / steps
+    # the library default is what is reported
     ms = time_loop(ctx, lambda: A.apply(x, y, 1.0, True), steps, 3, ctx.finish)
     _, nnz = gen.poisson_nnz(3, n)
     t = ms * 1e-3 / steps

@@ -24,16 +24,17 @@ if "--one" in sys.argv:
     ctx.finish()
     sys.exit(0)
 out = {}
-for kernel in (2, 3):
+for kernel in (3,):
     vx.set_param("ccsr.kernel", kernel)
     for append in (True, False):
         ms = time_loop(ctx, lambda: A.apply(x, y, 1.0, append), 40, 3, ctx.finish) / 40
         out[f"kernel={kernel},append={append}"] = {"ms": ms, "gbs_compulsory": N * (25 if append else 17) / (ms * 1e-3) / 1e9}
 vx.set_param("ccsr.kernel", 1)
-for threads in (256, 1024):
+for hoist in (0, 1):
     for batch in (1, 8):
-        vx.set_param("ccsr.threads", threads)
-        vx.set_param("ccsr.batch", batch)
-        ms = time_loop(ctx, lambda: A.apply(x, y, 1.0, True), 40, 3, ctx.finish) / 40
-        out[f"threads={threads},batch={batch}"] = {"ms": ms, "gbs_compulsory": N * 25 / (ms * 1e-3) / 1e9}
+        for append in (True, False):
+            vx.set_param("ccsr.hoist", hoist)
+            vx.set_param("ccsr.batch", batch)
+            ms = time_loop(ctx, lambda: A.apply(x, y, 1.0, append), 40, 3, ctx.finish) / 40
+            out[f"hoist={hoist},batch={batch},append={append}"] = {"ms": ms, "gbs_compulsory": N * (25 if append else 17) / (ms * 1e-3) / 1e9}
 print(json.dumps(out, indent=1))

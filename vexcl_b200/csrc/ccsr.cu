@@ -35,25 +35,31 @@ template <> __device__ __forceinline__ float c_add<float>(float a, float b) { re
 constexpr size_t CCSR_SMEM_LIMIT = 40 * 1024;
 constexpr long CCSR_DEFAULT_KERNEL = 1;
 
-template <class T, class I, bool SMEM, int CCSR_THREADS, int CCSR_BATCH>
+template <class T, class I, bool SMEM, int CCSR_THREADS, int CCSR_BATCH, bool HOIST>
 __global__ void __launch_bounds__(CCSR_THREADS) ccsr_kernel(size_t n, int m, int nnz, const I *__restrict__ idx,
                                                             const int *__restrict__ row, const int *__restrict__ col,
                                                             const T *__restrict__ val, const T *__restrict__ x, T *y,
                                                             T alpha, int append) {
     extern __shared__ __align__(16) unsigned char smem[];
     const T *vs = val; const int *cs = col, *rs = row;
+    const size_t i = (size_t)blockIdx.x * CCSR_THREADS + threadIdx.x;
+    // HOIST: the two loads that depend on nothing (idx[i], and y[i] when appending) are issued before the table is
+    // staged, so that a block waits for one DRAM round trip + the gathers instead of table -> idx -> gathers -> y.
+    int u = 0; T yo = T(0);
+    if (HOIST && i < n) { u = (int)idx[i]; if (append) yo = y[i]; }
     if (SMEM) {
         T *v = reinterpret_cast<T *>(smem);
         int *c = reinterpret_cast<int *>(v + nnz);
         int *r = c + nnz;
+#pragma unroll 1
         for (int j = threadIdx.x; j < nnz; j += CCSR_THREADS) { v[j] = val[j]; c[j] = col[j]; }
+#pragma unroll 1
         for (int j = threadIdx.x; j <= m; j += CCSR_THREADS) r[j] = row[j];
         __syncthreads();
         vs = v; cs = c; rs = r;
     }
-    const size_t i = (size_t)blockIdx.x * CCSR_THREADS + threadIdx.x;
     if (i >= n) return;
-    const int u = (int)idx[i];
+    if (!HOIST) u = (int)idx[i];
     T sum = T(0);
     // gathers of up to CCSR_BATCH entries are issued together (one dependent load per thread would leave the kernel
     // latency-bound: measured 2.5 TB/s of compulsory traffic on the 7-point stencil); products are then accumulated
@@ -67,7 +73,8 @@ __global__ void __launch_bounds__(CCSR_THREADS) ccsr_kernel(size_t n, int m, int
         for (int k = 0; k < CCSR_BATCH; ++k) if (j + k < e) sum = c_add<T>(sum, c_mul<T>(vs[j + k], xv[k]));
     }
     const T v = c_mul<T>(alpha, sum);
-    y[i] = append ? c_add<T>(y[i], v) : v;
+    if (HOIST) y[i] = append ? c_add<T>(yo, v) : v;
+    else y[i] = append ? c_add<T>(y[i], v) : v;
 }
 
 // Variant 2/3 (ccsr.kernel = 2 | 3).  ncu on variant 1 (profiles/r01_ncu_ccsr.md): DRAM 37 %, L2 24 %, L1 54 %, issue 56 %,
@@ -130,15 +137,15 @@ static long long read_int(const void *p, int bytes, bool is_signed, size_t k) {
     return is_signed ? (long long)((const int64_t *)p)[k] : (long long)((const uint64_t *)p)[k];
 }
 
-template <class T, class I, int THREADS, int BATCH>
+template <class T, class I, int THREADS, int BATCH, bool HOIST>
 static int launch_cfg(const vexb_ccsr *A, cudaStream_t st, const T *x, T *y, T alpha, int append) {
     const unsigned blocks = (unsigned)((A->n + THREADS - 1) / THREADS);
-    if (A->table_in_smem) {
+    if (A->table_in_smem && param("ccsr.smem", 1)) {
         const size_t smem = A->nnz * (sizeof(T) + sizeof(int)) + (A->m + 1) * sizeof(int);
-        ccsr_kernel<T, I, true, THREADS, BATCH><<<blocks, THREADS, smem, st>>>(A->n, (int)A->m, (int)A->nnz, (const I *)A->idx, A->row, A->col,
+        ccsr_kernel<T, I, true, THREADS, BATCH, HOIST><<<blocks, THREADS, smem, st>>>(A->n, (int)A->m, (int)A->nnz, (const I *)A->idx, A->row, A->col,
                                                                              (const T *)A->val, x, y, alpha, append);
     } else {
-        ccsr_kernel<T, I, false, THREADS, BATCH><<<blocks, THREADS, 0, st>>>(A->n, (int)A->m, (int)A->nnz, (const I *)A->idx, A->row, A->col,
+        ccsr_kernel<T, I, false, THREADS, BATCH, HOIST><<<blocks, THREADS, 0, st>>>(A->n, (int)A->m, (int)A->nnz, (const I *)A->idx, A->row, A->col,
                                                                            (const T *)A->val, x, y, alpha, append);
     }
     VEXB_LAUNCHED();
@@ -158,14 +165,15 @@ static int launch2(const vexb_ccsr *A, cudaStream_t st, const T *x, T *y, T alph
 
 template <class T, class I>
 static int launch(const vexb_ccsr *A, cudaStream_t st, const T *x, T *y, T alpha, int append) {
-    // tunables (vexb_set_param): ccsr.kernel = 1 | 2 | 3; for kernel 1: ccsr.threads = 256 | 1024, ccsr.batch = 8 | 1
+    // tunables (vexb_set_param): ccsr.kernel = 1 | 2 | 3; for kernel 1: ccsr.threads = 256 | 1024, ccsr.batch = 8 | 1, ccsr.hoist = 1 | 0, ccsr.smem = 1 | 0
     long kernel = param("ccsr.kernel", 0);
     if (kernel <= 0) kernel = CCSR_DEFAULT_KERNEL;
     if (kernel >= 2 && A->nnz * sizeof(Entry<T>) + (A->m + 1) * sizeof(int) <= CCSR_SMEM_LIMIT)
         return kernel == 3 ? launch2<T, I, 2>(A, st, x, y, alpha, append) : launch2<T, I, 1>(A, st, x, y, alpha, append);
-    const long threads = param("ccsr.threads", 256), batch = param("ccsr.batch", 8);
-    if (threads == 1024) return batch == 1 ? launch_cfg<T, I, 1024, 1>(A, st, x, y, alpha, append) : launch_cfg<T, I, 1024, 8>(A, st, x, y, alpha, append);
-    return batch == 1 ? launch_cfg<T, I, 256, 1>(A, st, x, y, alpha, append) : launch_cfg<T, I, 256, 8>(A, st, x, y, alpha, append);
+    const long threads = param("ccsr.threads", 256), batch = param("ccsr.batch", 8), hoist = param("ccsr.hoist", 1);
+    if (threads == 1024) return launch_cfg<T, I, 1024, 8, true>(A, st, x, y, alpha, append);
+    if (!hoist) return batch == 1 ? launch_cfg<T, I, 256, 1, false>(A, st, x, y, alpha, append) : launch_cfg<T, I, 256, 8, false>(A, st, x, y, alpha, append);
+    return batch == 1 ? launch_cfg<T, I, 256, 1, true>(A, st, x, y, alpha, append) : launch_cfg<T, I, 256, 8, true>(A, st, x, y, alpha, append);
 }
 
 template <class T>
