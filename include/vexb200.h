@@ -22,6 +22,8 @@
  *   vexb_spmv           <- SpMatCSR / SpMatHELL ctor + mul_local/mul_remote
  *                          (vexcl/spmat/csr.inl:45-209, hybrid_ell.inl:53-330)
  *   vexb_dspmat_*       <- SpMat ctor + SpMat::apply (vexcl/spmat.hpp:71-185)
+ *   vexb_ccsr_*         <- SpMatCCSR ctor + its generated product function
+ *                          (vexcl/spmat/ccsr.hpp:70-78, :176-201)
  *   vexb_comm_*         <- the host-staged D2H/H2D halo and the host fold of
  *                          reduction partials (spmat.hpp:149-176,
  *                          reductor.hpp:412-436), moved to NCCL over NVLink.
