@@ -395,6 +395,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             extra["ccsr_spmv"] = bench_ccsr(ctx, vx, args, peak)
         except vx.VexbError as e:
             extra["ccsr_spmv"] = {"error": str(e)}
+        try:
+            extra["stencil"] = bench_stencil(ctx, vx, args, peak)
+        except Exception as e:                                 # first measured by the round-end run: never lose the line
+            extra["stencil"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             cpu_base, y_cpu = cpu_baseline_sample()
             import oracle                      # checker only: parity of the timed kernel on the oracle's x
@@ -506,6 +510,21 @@ def bench_ccsr(ctx, vx, args, peak):
             "gbs_by_reference_formula": (nnz * 20 + 4 * N * 8) / t / 1e9,
             "note": "y += A*x; compulsory bytes = (1-byte idx + x + y in + y out) per row; the reference's own figure "
                     "(benchmark.cpp:563) counts the matrix as if it were CSR"}
+
+
+def bench_stencil(ctx, vx, args, peak):
+    """examples/benchmark.cpp:281-349: b = a * s with a 21-point stencil of 1/21; N = 2^26 doubles here (the reference
+    uses 2^20, whose 16 MB working set would sit in L2)."""
+    n, width = 1 << 26, 21
+    S = vx.stencil(ctx, np.full(width, 1.0 / width), width // 2)
+    a, b = vx.vector(ctx, n), vx.vector(ctx, n)
+    a.assign(vx.ElementIndex() * (1.0 / n) + 0.5)
+    steps = max(10, min(args.steps, 40))
+    ms = time_loop(ctx, lambda: S.apply(a, b, 1.0, False), steps, 3, ctx.finish)
+    t = ms * 1e-3 / steps
+    return {"n": n, "width": width, "ms": ms / steps, "gbs_compulsory": 16 * n / t / 1e9, "frac_of_peak": 16 * n / t / 1e9 / peak,
+            "gflops": 2.0 * width * n / t / 1e9, "gbs_by_reference_formula": 2.0 * width * n * 8 / t / 1e9,
+            "note": "compulsory bytes = x read once + y written once; the reference's figure (benchmark.cpp:308) counts every tap as a memory access"}
 
 
 def bench_vectors(ctx, vx, args, peak):

@@ -390,6 +390,22 @@ int vexb_ccsr_get_info(const vexb_ccsr *A, vexb_ccsr_info *info);
 int vexb_ccsr_spmv(int dev, void *stream, const vexb_ccsr *A, const void *x, void *y, double alpha, int append);
 
 /* ------------------------------------------------------------------------
+ * Stencil convolution: vex::stencil<T> (vexcl/stencil.hpp:168-330), one device
+ * slice per call:
+ *   y[i] (=|+=) alpha * sum_{k<width} s[k] * X(i + k - center)
+ * X = the slice x[0..n) extended by `left` (the `center` elements before it)
+ * and `right` (the width-1-center elements after it); a NULL side clamps to the
+ * slice's first / last element (the ends of the whole vector).  s, x, left,
+ * right, y are device pointers of `dtype` (VEXB_F64 or VEXB_F32).
+ * vexb_copy_peer moves halo pieces between devices (replaces the D2H/H2D
+ * staging of stencil_base::exchange_halos, stencil.hpp:86-150).
+ * ---------------------------------------------------------------------- */
+int vexb_stencil_apply(int dev, void *stream, int dtype, const void *s, int width, int center,
+                       const void *x, size_t n, const void *left, const void *right,
+                       void *y, double alpha, int append);
+int vexb_copy_peer(int dst_dev, void *dst, int src_dev, const void *src, size_t bytes, void *stream);
+
+/* ------------------------------------------------------------------------
  * Distributed SpMat part: the slice of a vex::SpMat owned by one device
  * (spmat.hpp:71-106 ctor body for one d, :120-185 apply).
  * `col` holds GLOBAL column ids for the strip's rows, indexed by ptr values

@@ -1,0 +1,109 @@
+#ifndef VEXCL_STENCIL_HPP
+#define VEXCL_STENCIL_HPP
+/*
+ * vex::stencil<T> (vexcl/stencil.hpp:168-330): convolution of a vector with a small stencil,
+ *     y = x * s;   y += x * s;   y = 42 * (x * s);   y = x * s + x * s;        (also for multivectors)
+ *     y[i] = sum_k s[k] * x[clamp(i + k - center, 0, n-1)]
+ *
+ * The product is libvexb200's stencil_kernel (csrc/stencil.cu).  With several device slices the elements a slice
+ * needs from its neighbours are copied device to device into a per-slice halo buffer before the launch (the reference
+ * stages them through the host, stencil.hpp:86-150); like the reference, the exchange waits for the queues on both
+ * sides.  The user-defined StencilOperator (VEX_STENCIL_OPERATOR, stencil.hpp:510-680) is not provided.
+ */
+#include <algorithm>
+#include <initializer_list>
+#include "vector.hpp"
+#include "multivector.hpp"
+
+namespace vex {
+
+template <typename T>
+class stencil {
+    public:
+        typedef T value_type;
+
+        /// queue list, stencil values, index of the center element (stencil.hpp:179-228).
+        stencil(const std::vector<backend::command_queue> &queue, const std::vector<T> &st, unsigned center)
+            : queue(queue) { init(st.data(), st.size(), center); }
+        template <class Iterator>
+        stencil(const std::vector<backend::command_queue> &queue, Iterator begin, Iterator end, unsigned center)
+            : queue(queue) { std::vector<T> st(begin, end); init(st.data(), st.size(), center); }
+        stencil(const std::vector<backend::command_queue> &queue, std::initializer_list<T> list, unsigned center)
+            : queue(queue) { std::vector<T> st(list); init(st.data(), st.size(), center); }
+
+        /// y = alpha * (x * s)  or  y += alpha * (x * s)   (stencil<T>::apply, stencil.hpp:258-330).
+        void apply(const vex::vector<T> &x, vex::vector<T> &y, T alpha = 1, bool append = false) const {
+            precondition(x.size() == y.size(), "stencil: vectors differ in size");
+            precondition(x.nparts() == queue.size() && y.nparts() == queue.size(), "stencil: vectors live on other queues");
+            std::vector<const T*> left(queue.size(), nullptr), right(queue.size(), nullptr);
+            exchange_halos(x, left, right);
+            for (unsigned d = 0; d < queue.size(); ++d)
+                VEXB_CHECKED(vexb_stencil_apply(queue[d].ordinal(), queue[d].raw(), dtype_of<T>::value, s[d].raw(), width, lhalo,
+                                                x(d).raw(), x.part_size(d), left[d], right[d], y(d).raw(),
+                                                static_cast<double>(alpha), append));
+        }
+        unsigned size() const { return static_cast<unsigned>(width); }
+    private:
+        std::vector<backend::command_queue> queue;
+        std::vector<backend::device_vector<T>> s, dbuf;
+        int width = 0, lhalo = 0, rhalo = 0;
+
+        void init(const T *st, size_t n, unsigned center) {
+            precondition(!queue.empty() && n >= 1 && center < n, "stencil needs width >= 1 and center < width");   // stencil.hpp:70-74
+            width = static_cast<int>(n); lhalo = static_cast<int>(center); rhalo = width - lhalo - 1;
+            for (unsigned d = 0; d < queue.size(); ++d) {
+                s.emplace_back(queue[d], n, st);
+                dbuf.emplace_back(queue[d], static_cast<size_t>(width));          // one more than needed, never empty (stencil.hpp:81-82)
+            }
+            for (auto &q : queue) q.finish();
+        }
+
+        /// Copy global elements [g0, g1) of x into dbuf[d] at element offset `at`.
+        void gather(const vex::vector<T> &x, unsigned d, size_t at, size_t g0, size_t g1) const {
+            for (unsigned p = 0; p < queue.size(); ++p) {
+                const size_t a = std::max(g0, x.part_start(p)), b = std::min(g1, x.part_start(p) + x.part_size(p));
+                if (a < b)
+                    VEXB_CHECKED(vexb_copy_peer(queue[d].ordinal(), dbuf[d].raw_ptr() + at + (a - g0), queue[p].ordinal(),
+                                                x(p).raw_ptr() + (a - x.part_start(p)), (b - a) * sizeof(T), queue[d].raw()));
+            }
+        }
+        void fill(unsigned d, size_t at, size_t count, T value) const {
+            std::vector<T> h(count, value);
+            dbuf[d].write(queue[d], at, count, h.data(), true);
+        }
+
+        void exchange_halos(const vex::vector<T> &x, std::vector<const T*> &left, std::vector<const T*> &right) const {
+            if (queue.size() <= 1 || width <= 1) return;                          // stencil.hpp:89
+            const size_t n = x.size();
+            for (auto &q : queue) q.finish();                                     // the neighbours' slices must be complete
+            for (unsigned d = 0; d < queue.size(); ++d) {
+                const size_t start = x.part_start(d), size = x.part_size(d);
+                if (!size) continue;
+                if (start > 0 && lhalo > 0) {
+                    const size_t have = std::min<size_t>(start, lhalo);           // elements that exist before this slice
+                    if (have < static_cast<size_t>(lhalo)) fill(d, 0, lhalo - have, x[0]);
+                    gather(x, d, lhalo - have, start - have, start);
+                    left[d] = dbuf[d].raw_ptr();
+                }
+                if (start + size < n && rhalo > 0) {
+                    const size_t g0 = start + size, g1 = std::min(g0 + rhalo, n);
+                    gather(x, d, lhalo, g0, g1);
+                    if (g1 - g0 < static_cast<size_t>(rhalo)) fill(d, lhalo + (g1 - g0), rhalo - (g1 - g0), x[n - 1]);
+                    right[d] = dbuf[d].raw_ptr() + lhalo;
+                }
+            }
+            for (auto &q : queue) q.finish();                                     // nobody overwrites x while a neighbour copies from it
+        }
+};
+
+template <typename T>
+additive_operator<stencil<T>, vector<T>> operator*(const stencil<T> &s, const vector<T> &x) { return additive_operator<stencil<T>, vector<T>>(s, x); }
+template <typename T>
+additive_operator<stencil<T>, vector<T>> operator*(const vector<T> &x, const stencil<T> &s) { return additive_operator<stencil<T>, vector<T>>(s, x); }
+template <typename T, size_t N>
+additive_operator<stencil<T>, multivector<T, N>> operator*(const stencil<T> &s, const multivector<T, N> &x) { return additive_operator<stencil<T>, multivector<T, N>>(s, x); }
+template <typename T, size_t N>
+additive_operator<stencil<T>, multivector<T, N>> operator*(const multivector<T, N> &x, const stencil<T> &s) { return additive_operator<stencil<T>, multivector<T, N>>(s, x); }
+
+} // namespace vex
+#endif

@@ -16,6 +16,7 @@
 #include "reductor.hpp"
 #include "spmat.hpp"
 #include "spmat/ccsr.hpp"
+#include "stencil.hpp"
 #include "sparse/product.hpp"
 #include "sparse/matrix.hpp"
 #include "sparse/distributed.hpp"

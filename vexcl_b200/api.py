@@ -200,8 +200,8 @@ class Node:
     def __sub__(self, o): return self._bin("SUB", o)
     def __rsub__(self, o): return self._bin("SUB", o, True)
     def __mul__(self, o):
-        if isinstance(o, SpMat):
-            return NotImplemented
+        if isinstance(o, (SpMat, stencil)):
+            return NotImplemented                      # x * A is not defined; x * s is stencil.__rmul__
         return self._bin("MUL", o)
     def __rmul__(self, o): return self._bin("MUL", o, True)
     def __truediv__(self, o): return self._bin("DIV", o)
@@ -821,6 +821,96 @@ class SpMatCCSR:
             raise ValueError("SpMatCCSR::apply: vector sizes do not match the matrix")
         k = self.ctx.local[0]
         L.check(L.lib().vexb_ccsr_spmv(self.ctx.devs[k], self.ctx.streams[k], self.h, x.bufs[k], y.bufs[k], float(alpha), int(append)))
+        return y
+
+
+class stencil:
+    """vex::stencil<T> (stencil.hpp:168-330): `y = x * s`, `y += x * s`, `y = 42 * (x * s)`, ...
+    y[i] = sum_k s[k] * x[clamp(i + k - center)]; with several slices the neighbours' edge elements are copied
+    device to device into per-slice halo buffers first (stencil_base::exchange_halos, stencil.hpp:86-150)."""
+
+    def __init__(self, ctx: Context, s, center: int, dtype=np.float64):
+        if ctx.is_distributed:
+            raise NotImplementedError("stencil: one process per GPU is not wired up yet")
+        self.ctx = ctx
+        self.s = np.ascontiguousarray(s, dtype=dtype)
+        self.width, self.center = int(self.s.size), int(center)
+        if not (self.width >= 1 and 0 <= self.center < self.width):
+            raise ValueError("stencil needs width >= 1 and 0 <= center < width")      # stencil.hpp:70-74
+        self.lhalo, self.rhalo = self.center, self.width - self.center - 1
+        self.dtype = _vdt(self.s.dtype)
+        lib, es = L.lib(), self.s.dtype.itemsize
+        self.sdev, self.halo = {}, {}
+        for k in ctx.local:
+            p, h = C.c_void_p(), C.c_void_p()
+            L.check(lib.vexb_malloc(ctx.devs[k], self.width * es, C.byref(p)))
+            L.check(lib.vexb_h2d(ctx.devs[k], p, self.s.ctypes.data, self.width * es, ctx.streams[k], 1))
+            L.check(lib.vexb_malloc(ctx.devs[k], max(self.width - 1, 1) * es, C.byref(h)))
+            self.sdev[k], self.halo[k] = p, h
+
+    def __del__(self):
+        try:
+            for k in self.sdev:
+                L.lib().vexb_free(self.ctx.devs[k], self.sdev[k])
+                L.lib().vexb_free(self.ctx.devs[k], self.halo[k])
+        except Exception:
+            pass
+
+    def __mul__(self, x):
+        return SpMVTerm(self, x) if isinstance(x, vector) else NotImplemented
+    __rmul__ = __mul__
+
+    def _fill(self, k, ptr, count, value):
+        low = _Lowering(k, 0)
+        low.size = count
+        low.lower(Scalar(value, self.dtype))
+        L.check(L.lib().vexb_eval(self.ctx.devs[k], self.ctx.streams[k], ptr, self.dtype, L.SET, C.byref(low.e), count, 0))
+
+    def _gather(self, x: vector, k: int, dst_off: int, g0: int, g1: int):
+        """Copy global elements [g0, g1) of x into slice k's halo buffer at element offset dst_off."""
+        ctx, es, lib = self.ctx, self.s.dtype.itemsize, L.lib()
+        for p in range(ctx.nparts):
+            a, b = max(g0, x.part_start(p)), min(g1, x.part_start(p) + x.part_size(p))
+            if a < b:
+                L.check(lib.vexb_copy_peer(ctx.devs[k], C.c_void_p(self.halo[k].value + (dst_off + a - g0) * es), ctx.devs[p],
+                                           C.c_void_p(x.bufs[p].value + (a - x.part_start(p)) * es), (b - a) * es, ctx.streams[k]))
+
+    def exchange_halos(self, x: vector):
+        """Returns {slice: (left pointer or None, right pointer or None)}."""
+        ctx, n, es = self.ctx, x.n, self.s.dtype.itemsize
+        sides = {k: (None, None) for k in ctx.local}
+        if ctx.nparts <= 1 or self.width == 1:
+            return sides
+        ctx.finish()                                     # the neighbours' slices must be complete (stencil.hpp:113)
+        for k in ctx.local:
+            start, size = x.part_start(k), x.part_size(k)
+            if not size:
+                continue
+            left = right = None
+            if start > 0 and self.lhalo:
+                g0 = start - self.lhalo
+                if g0 < 0:                               # fewer elements before this slice than the stencil reaches
+                    self._fill(k, self.halo[k], -g0, x[0])
+                self._gather(x, k, max(0, -g0), max(g0, 0), start)
+                left = self.halo[k]
+            if start + size < n and self.rhalo:
+                g0, g1 = start + size, min(start + size + self.rhalo, n)
+                self._gather(x, k, self.lhalo, g0, g1)
+                if g1 - g0 < self.rhalo:
+                    self._fill(k, C.c_void_p(self.halo[k].value + (self.lhalo + g1 - g0) * es), self.rhalo - (g1 - g0), x[n - 1])
+                right = C.c_void_p(self.halo[k].value + self.lhalo * es)
+            sides[k] = (left, right)
+        ctx.finish()                                     # nobody may overwrite x while a neighbour still copies from it
+        return sides
+
+    def apply(self, x: vector, y: vector, alpha: float = 1.0, append: bool = False):
+        if x.n != y.n or x.dtype != self.dtype or y.dtype != self.dtype:
+            raise ValueError("stencil: vectors must have the stencil's type and equal sizes")
+        sides = self.exchange_halos(x)
+        for k in self.ctx.local:
+            left, right = sides[k]
+            L.check(L.lib().vexb_stencil_apply(self.ctx.devs[k], self.ctx.streams[k], self.dtype, self.sdev[k], self.width,
+                                               self.center, x.bufs[k], x.part_size(k), left, right, y.bufs[k], float(alpha), int(append)))
         return y
 
 

@@ -1,0 +1,155 @@
+// vex::stencil<T> convolution (vexcl/stencil.hpp:168-330; semantics as the reference benchmark's CPU check,
+// examples/benchmark.cpp:318-327):
+//     y[i] (=|+=) alpha * sum_{k < width} s[k] * X(i + k - center),     X(j) = x[clamp(j, 0, n-1)] over the WHOLE vector.
+// One device slice per call; positions left of the slice come from `left` (the `center` elements before it) and
+// positions right of it from `right` (the `width-1-center` elements after it) when the slice is not at an end of the
+// vector, otherwise they clamp to the slice's first / last element.
+//
+// B200 design.  16 B/element of compulsory traffic (x once, y once; +8 for `+=`) against 2*width FP64 instructions
+// (products and sums are rounded separately, in tap order, like the reference loop): at width 21 the two are about
+// balanced, so neither shared memory nor issue slots may cost more than that.  Hence
+//   * a block stages its x window (1024 outputs + width-1 neighbours) and the taps in shared memory once;
+//   * a thread owns EIGHT CONSECUTIVE outputs and slides a 16-element register window over the taps in chunks of 8:
+//     per chunk 8 window loads + 8 tap loads (broadcast) feed 64 multiply-adds, 4x fewer shared-memory reads per
+//     product than one-output-per-thread;
+//   * the window is stored with one pad word per 8 elements, so the stride-8 accesses of neighbouring lanes fall in
+//     different banks (stride 9);
+//   * a thread's 8 results leave as 256-bit stores (and `+=` reads y with 256-bit loads).
+#include "common.cuh"
+#include "shapes.cuh"
+
+namespace vexb {
+namespace {
+
+constexpr int ST_THREADS = 128;
+constexpr int ST_E = 8;                                  // consecutive outputs per thread
+constexpr int ST_B = ST_THREADS * ST_E;                  // outputs per block
+
+__host__ __device__ __forceinline__ int st_pad(int p) { return p + (p >> 3); }
+__host__ __device__ __forceinline__ int st_ceil8(int w) { return (w + 7) & ~7; }
+
+template <class T>
+__global__ void __launch_bounds__(ST_THREADS) stencil_kernel(const T *__restrict__ s, int width, int center,
+                                                             const T *__restrict__ x, long long n,
+                                                             const T *__restrict__ left, const T *__restrict__ right,
+                                                             T *y, T alpha, int append, int vec_io) {
+    typedef Arith<T> A;
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    const int wlen = ST_B + st_ceil8(width);             // window positions staged (those past ST_B+width-2 are never used in a product)
+    T *win = reinterpret_cast<T *>(st_smem);
+    T *taps = win + st_pad(wlen) + 1;
+    const long long b0 = (long long)blockIdx.x * ST_B;
+    const int rhalo = width - 1 - center;
+
+    // ---- stage the window: position p holds X(b0 - center + p) --------------------------------------------------
+    for (int p = threadIdx.x; p < wlen; p += ST_THREADS) {
+        const long long j = b0 - center + p;
+        T v;
+        if (j < 0) v = left ? left[center + j] : x[0];
+        else if (j >= n) {
+            const long long r = j - n;
+            v = (right && rhalo > 0) ? right[r < rhalo ? r : rhalo - 1] : x[n - 1];
+        } else v = x[j];
+        win[st_pad(p)] = v;
+    }
+    for (int k = threadIdx.x; k < st_ceil8(width); k += ST_THREADS) taps[k] = k < width ? s[k] : T(0);
+    __syncthreads();
+
+    const int o = threadIdx.x * ST_E;                     // first output of this thread within the block
+    if (b0 + o >= n) return;
+    T sum[ST_E], lo[8], hi[8];
+#pragma unroll
+    for (int e = 0; e < ST_E; ++e) sum[e] = T(0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lo[j] = win[st_pad(o + j)];
+    for (int kk = 0; kk < width; kk += 8) {
+        const int rem = width - kk;                       // taps left (>= 1); block-uniform
+        T sk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { hi[j] = win[st_pad(o + kk + 8 + j)]; sk[j] = taps[kk + j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < rem) {
+#pragma unroll
+                for (int e = 0; e < ST_E; ++e) sum[e] = A::add(sum[e], A::mul(sk[j], (e + j < 8) ? lo[e + j] : hi[e + j - 8]));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lo[j] = hi[j];
+    }
+
+    // ---- y (=|+=) alpha * sum -------------------------------------------------------------------------------------
+    const long long i0 = b0 + o;
+    constexpr int PER = Lanes<T>::E;                      // elements per 256-bit access: 4 doubles, 8 floats
+    if (vec_io && i0 + ST_E <= n) {
+#pragma unroll
+        for (int q = 0; q < ST_E / PER; ++q) {
+            Vec256 out = {};
+            if (append) {
+                const Vec256 old = ldg256(y + i0 + q * PER);
+#pragma unroll
+                for (int e = 0; e < PER; ++e) Lanes<T>::set(out, e, A::add(Lanes<T>::get(old, e), A::mul(alpha, sum[q * PER + e])));
+            } else {
+#pragma unroll
+                for (int e = 0; e < PER; ++e) Lanes<T>::set(out, e, A::mul(alpha, sum[q * PER + e]));
+            }
+            stg256(y + i0 + q * PER, out);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < ST_E; ++e) {
+            if (i0 + e < n) { const T v = A::mul(alpha, sum[e]); y[i0 + e] = append ? A::add(y[i0 + e], v) : v; }
+        }
+    }
+}
+
+template <class T>
+static int stencil_launch(int dev, cudaStream_t st, const T *s, int width, int center, const T *x, size_t n,
+                          const T *left, const T *right, T *y, T alpha, int append) {
+    const int wlen = ST_B + st_ceil8(width);
+    const size_t smem = ((size_t)st_pad(wlen) + 1 + st_ceil8(width)) * sizeof(T);
+    if (smem > 200 * 1024) VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "stencil of %d taps does not fit in shared memory", width);
+    static std::atomic<unsigned long long> attr_set[2];
+    const int ti = sizeof(T) == 8 ? 0 : 1;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (smem > 48 * 1024 && !(attr_set[ti].load() & bit)) {
+        VEXB_CUDA(cudaFuncSetAttribute(stencil_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[ti].fetch_or(bit);
+    }
+    const unsigned blocks = (unsigned)((n + ST_B - 1) / ST_B);
+    const int vec_io = aligned32(y) ? 1 : 0;
+    stencil_kernel<T><<<blocks, ST_THREADS, smem, st>>>(s, width, center, x, (long long)n, left, right, y, alpha, append, vec_io);
+    VEXB_LAUNCHED();
+    return VEXB_OK;
+}
+
+} // namespace
+} // namespace vexb
+
+using namespace vexb;
+
+extern "C" int vexb_stencil_apply(int dev, void *stream, int dtype, const void *s, int width, int center,
+                                  const void *x, size_t n, const void *left, const void *right,
+                                  void *y, double alpha, int append) {
+    VEXB_CHECK(dtype == VEXB_F64 || dtype == VEXB_F32, "stencil values must be float or double");
+    VEXB_CHECK(width >= 1 && center >= 0 && center < width, "stencil needs width >= 1 and 0 <= center < width");
+    if (!n) return VEXB_OK;
+    VEXB_CHECK(s && x && y, "null pointer");
+    VEXB_CHECK(n < ((size_t)1 << 40), "slice too long");
+    DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == VEXB_F64)
+        return stencil_launch<double>(dev, st, (const double *)s, width, center, (const double *)x, n, (const double *)left,
+                                      (const double *)right, (double *)y, alpha, append);
+    return stencil_launch<float>(dev, st, (const float *)s, width, center, (const float *)x, n, (const float *)left,
+                                 (const float *)right, (float *)y, (float)alpha, append);
+}
+
+extern "C" int vexb_copy_peer(int dst_dev, void *dst, int src_dev, const void *src, size_t bytes, void *stream) {
+    if (!bytes) return VEXB_OK;
+    VEXB_CHECK(dst && src, "null pointer");
+    DeviceGuard g(dst_dev); VEXB_CHECK(g.ok, "cannot select device %d", dst_dev);
+    if (dst_dev == src_dev) VEXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    else VEXB_CUDA(cudaMemcpyPeerAsync(dst, dst_dev, src, src_dev, bytes, (cudaStream_t)stream));
+    return VEXB_OK;
+}
