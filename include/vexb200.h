@@ -388,6 +388,12 @@ int vexb_ccsr_create(int dev, void *stream, size_t n, size_t m, const void *idx,
 int vexb_ccsr_destroy(vexb_ccsr *A);
 int vexb_ccsr_get_info(const vexb_ccsr *A, vexb_ccsr_info *info);
 int vexb_ccsr_spmv(int dev, void *stream, const vexb_ccsr *A, const void *x, void *y, double alpha, int append);
+/* Source of the matrix-specialised product kernel (tunable "ccsr.jit"; the unique rows become code, compiled by
+ * NVRTC at first use -- the counterpart of the reference's generated "<prm>_spmv" function, ccsr.hpp:176-201).
+ * Host-only: m unique rows, row[m+1] offsets, col/val entries; idx_bytes = device width of idx (1, 2 or 4).
+ * compile != 0 also runs NVRTC for sm_100a (no device needed).  *len in: capacity, out: bytes needed. */
+int vexb_ccsr_jit_source(size_t m, const int32_t *row, const int32_t *col, const void *val, int val_dtype,
+                         int idx_bytes, char *buf, size_t *len, int compile);
 
 /* ------------------------------------------------------------------------
  * Stencil convolution: vex::stencil<T> (vexcl/stencil.hpp:168-330), one device

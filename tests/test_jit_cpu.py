@@ -72,6 +72,44 @@ def test_a_broken_body_is_reported_with_the_compiler_log(env):
         api.UserFunction(np.float64, "not an identifier", [], "return 1;")
 
 
+def _ccsr_source(L, row, col, val, idx_bytes=1, compile=True):
+    row, col = np.ascontiguousarray(row, np.int32), np.ascontiguousarray(col, np.int32)
+    val = np.ascontiguousarray(val)
+    dt = L.F64 if val.dtype == np.float64 else L.F32
+    n = C.c_size_t(0)
+    args = (row.size - 1, row.ctypes.data, col.ctypes.data, val.ctypes.data, dt, idx_bytes)
+    L.check(L.lib().vexb_ccsr_jit_source(*args, None, C.byref(n), 0))
+    buf = C.create_string_buffer(n.value + 256)
+    cap = C.c_size_t(len(buf))
+    L.check(L.lib().vexb_ccsr_jit_source(*args, buf, C.byref(cap), int(compile)))
+    return buf.value.decode()
+
+
+def test_ccsr_specialised_kernel_source_compiles(env):
+    """The matrix-specialised CCSR kernel (csrc/ccsr.cu, tunable ccsr.jit): unique rows become code.  NVRTC compiles it
+    for sm_100a without a device; running it is a GPU test (tests/test_gpu_ccsr.py, VEXB_RUN_UNVERIFIED in round 1)."""
+    vx, api, L, _ = env
+    from vexcl_b200 import gen
+    idx, row, col, val = gen.poisson_ccsr(32)
+    src = _ccsr_source(L, row, col, val)
+    assert "NVRTC: ok" in src and "vexb_ccsr_jit" in src and "const unsigned char *__restrict__ idx" in src
+    assert src.count("case ") == 2 and src.count("__ldg(") == 8
+    assert "__ldg(xi + (-1024))" in src and "__ldg(xi + (1024))" in src                   # +-n^2 as address immediates
+    assert float.fromhex(src.split("__dmul_rn(")[1].split(",")[0]) == 1.0                  # boundary row: 1 * x[i]
+    lits = [float.fromhex(t.split(",")[0]) for t in src.split("__dmul_rn(")[1:9]]
+    assert lits == list(val)                                                                # values survive exactly (hex literals)
+    # single precision, 2-byte idx, a row longer than one gather group, an empty row
+    rng = np.random.default_rng(2)
+    row = np.array([0, 0, 11, 14])
+    col = rng.integers(-50, 50, 14)
+    valf = rng.random(14).astype(np.float32)
+    src = _ccsr_source(L, row, col, valf, idx_bytes=2)
+    assert "NVRTC: ok" in src and "const unsigned short *__restrict__ idx" in src and "__fmul_rn(" in src
+    assert [np.float32(float.fromhex(t.split("f,")[0])) for t in src.split("__fmul_rn(")[1:15]] == list(valf)
+    with pytest.raises(vx.VexbError, match="too large"):
+        _ccsr_source(L, np.arange(41), np.zeros(40, np.int32), np.ones(40), compile=False)
+
+
 def test_unregistered_call_is_rejected(env):
     vx, api, L, fake_vec = env
     e = L.Expr()

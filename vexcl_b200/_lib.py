@@ -150,6 +150,7 @@ def lib():
         "vexb_ccsr_destroy": ([vp], i),
         "vexb_ccsr_get_info": ([vp, P(CcsrInfo)], i),
         "vexb_ccsr_spmv": ([i, vp, vp, vp, vp, d, i], i),
+        "vexb_ccsr_jit_source": ([sz, vp, vp, vp, i, i, C.c_char_p, P(sz), i], i),
         "vexb_stencil_apply": ([i, vp, i, vp, i, i, vp, sz, vp, vp, vp, d, i], i),
         "vexb_copy_peer": ([i, vp, i, vp, sz, vp], i),
         "vexb_dspmat_create": ([i, vp, i, vp, sz, vp, i, vp, i, vp, i, i, P(vp)], i),

@@ -12,14 +12,19 @@
 //   * one thread per row, consecutive threads on consecutive rows: every x access of a warp is one or two lines.
 // Products and sums are rounded separately and accumulated in storage order (no FMA), so the result is
 // bit-identical to the reference's loop compiled without contraction (oracle/ccsr.py).
+#include <algorithm>
+#include <string>
 #include <vector>
 #include "common.cuh"
+#include "jit.hpp"
 
 struct vexb_ccsr {
     int dev = 0, val_dtype = VEXB_F64, idx_bytes = 1;
     size_t n = 0, m = 0, nnz = 0, device_bytes = 0;
     void *idx = nullptr; int *row = nullptr; int *col = nullptr; void *val = nullptr;
     bool table_in_smem = true;
+    std::vector<int> hrow, hcol; std::vector<double> hval;    // host copy of the unique-row table (source of the specialised kernel)
+    void *jit_fn = nullptr; bool jit_failed = false;
 };
 
 namespace vexb {
@@ -34,6 +39,7 @@ template <> __device__ __forceinline__ float c_add<float>(float a, float b) { re
 
 constexpr size_t CCSR_SMEM_LIMIT = 40 * 1024;
 constexpr long CCSR_DEFAULT_KERNEL = 1;
+constexpr long CCSR_DEFAULT_JIT = 0;        // round 1: the specialised kernel compiles (tests/test_jit_cpu.py) but has not run on a GPU yet
 
 template <class T, class I, bool SMEM, int CCSR_THREADS, int CCSR_BATCH, bool HOIST>
 __global__ void __launch_bounds__(CCSR_THREADS) ccsr_kernel(size_t n, int m, int nnz, const I *__restrict__ idx,
@@ -176,6 +182,70 @@ static int launch(const vexb_ccsr *A, cudaStream_t st, const T *x, T *y, T alpha
     return batch == 1 ? launch_cfg<T, I, 256, 1, true>(A, st, x, y, alpha, append) : launch_cfg<T, I, 256, 8, true>(A, st, x, y, alpha, append);
 }
 
+// ---- matrix-specialised kernel (ccsr.jit = 1; NVRTC) ----------------------------------------------------------------------
+// The reference generates its CCSR product as source text per expression (ccsr.hpp:176-201) but still walks the row
+// table at run time.  Here the unique rows themselves become code: one `case` per unique row with the column offsets
+// as address immediates and the values as hexadecimal floating literals -- no table, no loop, no shared memory, about
+// 25 instructions per row instead of ~190.  Same operation order and rounding as ccsr_kernel (products and sums
+// separate, storage order), so the bits are identical.  Eligible when the table is small (CCSR_JIT_MAX_*).
+constexpr size_t CCSR_JIT_MAX_ROWS = 32, CCSR_JIT_MAX_NNZ = 256;
+
+static std::string ccsr_jit_source(int val_dtype, int idx_bytes, const std::vector<int> &row, const std::vector<int> &col,
+                                   const std::vector<double> &val) {
+    const bool f64 = val_dtype == VEXB_F64;
+    const char *T = f64 ? "double" : "float";
+    const char *I = idx_bytes == 1 ? "unsigned char" : idx_bytes == 2 ? "unsigned short" : "int";
+    const char *mul = f64 ? "__dmul_rn" : "__fmul_rn", *add = f64 ? "__dadd_rn" : "__fadd_rn";
+    std::string s;
+    char buf[256];
+    s += "// generated by libvexb200 (csrc/ccsr.cu) for one CCSR matrix: " + std::to_string(row.size() - 1) + " unique rows, " +
+         std::to_string(col.size()) + " entries\n";
+    snprintf(buf, sizeof(buf), "extern \"C\" __global__ void __launch_bounds__(256) vexb_ccsr_jit(unsigned long long n, const %s *__restrict__ idx,\n"
+                               "        const %s *__restrict__ x, %s *y, %s alpha, int append) {\n", I, T, T, T);
+    s += buf;
+    s += "    const unsigned long long i = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;\n"
+         "    if (i >= n) return;\n"
+         "    const int u = (int)idx[i];\n";
+    s += std::string("    ") + T + " yo = 0;\n    if (append) yo = y[i];\n";
+    s += std::string("    const ") + T + " *xi = x + i;\n    " + T + " sum = 0;\n    switch (u) {\n";
+    for (size_t u = 0; u + 1 < row.size(); ++u) {
+        s += "    case " + std::to_string(u) + ": {\n";
+        for (int base = row[u]; base < row[u + 1]; base += 8) {              // gathers in groups of 8, then the products in order
+            const int end = std::min(base + 8, row[u + 1]);
+            for (int j = base; j < end; ++j) {
+                snprintf(buf, sizeof(buf), "        const %s x%d = __ldg(xi + (%d));\n", T, j - row[u], col[j]);
+                s += buf;
+            }
+            for (int j = base; j < end; ++j) {
+                if (f64) snprintf(buf, sizeof(buf), "        sum = %s(sum, %s(%a, x%d));\n", add, mul, val[j], j - row[u]);
+                else snprintf(buf, sizeof(buf), "        sum = %s(sum, %s(%af, x%d));\n", add, mul, (double)(float)val[j], j - row[u]);
+                s += buf;
+            }
+        }
+        s += "    } break;\n";
+    }
+    s += "    default: break;\n    }\n";
+    s += std::string("    const ") + T + " v = " + mul + "(alpha, sum);\n";
+    s += std::string("    y[i] = append ? ") + add + "(yo, v) : v;\n}\n";
+    return s;
+}
+
+template <class T>
+static int launch_jit(vexb_ccsr *A, cudaStream_t st, const T *x, T *y, T alpha, int append, bool *done) {
+    *done = false;
+    if (A->jit_failed || A->m > CCSR_JIT_MAX_ROWS || A->nnz > CCSR_JIT_MAX_NNZ) return VEXB_OK;
+    if (!A->jit_fn) {
+        const std::string src = ccsr_jit_source(A->val_dtype, A->idx_bytes, A->hrow, A->hcol, A->hval);
+        if (jit_build(A->dev, src, "vexb_ccsr_jit", &A->jit_fn) != VEXB_OK) { A->jit_failed = true; return VEXB_OK; }   // generic kernel instead
+    }
+    unsigned long long n = A->n;
+    const void *idx = A->idx;
+    void *args[] = {&n, &idx, &x, &y, &alpha, &append};
+    VEXB_TRY(jit_launch(A->jit_fn, (unsigned)((A->n + 255) / 256), 256, 0, st, args));
+    *done = true;
+    return VEXB_OK;
+}
+
 template <class T>
 static int launch_idx(const vexb_ccsr *A, cudaStream_t st, const T *x, T *y, T alpha, int append) {
     switch (A->idx_bytes) {
@@ -218,6 +288,8 @@ extern "C" int vexb_ccsr_create(int dev, void *stream, size_t n, size_t m, const
         }
     auto *A = new vexb_ccsr();
     A->dev = dev; A->val_dtype = val_dtype; A->n = n; A->m = m; A->nnz = (size_t)nnz;
+    A->hrow = hrow; A->hcol = hcol; A->hval.resize((size_t)nnz);
+    for (long long j = 0; j < nnz; ++j) A->hval[(size_t)j] = val_dtype == VEXB_F64 ? ((const double *)val)[j] : (double)((const float *)val)[j];
     A->idx_bytes = m <= 256 ? 1 : m <= 65536 ? 2 : 4;
     A->table_in_smem = A->nnz * (dtype_size(val_dtype) + sizeof(int)) + (m + 1) * sizeof(int) <= CCSR_SMEM_LIMIT;
     std::vector<uint8_t> i8; std::vector<uint16_t> i16; std::vector<int32_t> i32;
@@ -268,6 +340,37 @@ extern "C" int vexb_ccsr_spmv(int dev, void *stream, const vexb_ccsr *A, const v
     VEXB_CHECK(x && y, "null vector");
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     cudaStream_t st = (cudaStream_t)stream;
+    if (param("ccsr.jit", CCSR_DEFAULT_JIT)) {
+        bool done = false;
+        vexb_ccsr *M = const_cast<vexb_ccsr *>(A);                    // lazily attaches the specialised kernel
+        if (A->val_dtype == VEXB_F64) VEXB_TRY(launch_jit<double>(M, st, (const double *)x, (double *)y, alpha, append, &done));
+        else VEXB_TRY(launch_jit<float>(M, st, (const float *)x, (float *)y, (float)alpha, append, &done));
+        if (done) return VEXB_OK;
+    }
     if (A->val_dtype == VEXB_F64) return launch_idx<double>(A, st, (const double *)x, (double *)y, alpha, append);
     return launch_idx<float>(A, st, (const float *)x, (float *)y, (float)alpha, append);
+}
+
+extern "C" int vexb_ccsr_jit_source(size_t m, const int32_t *row, const int32_t *col, const void *val, int val_dtype,
+                                    int idx_bytes, char *buf, size_t *len, int compile) {
+    VEXB_CHECK(len && row, "null argument");
+    VEXB_CHECK(val_dtype == VEXB_F64 || val_dtype == VEXB_F32, "CCSR values must be float or double");
+    VEXB_CHECK(idx_bytes == 1 || idx_bytes == 2 || idx_bytes == 4, "idx_bytes must be 1, 2 or 4");
+    VEXB_CHECK(m >= 1 && m <= CCSR_JIT_MAX_ROWS && row[0] == 0 && row[m] >= 0 && (size_t)row[m] <= CCSR_JIT_MAX_NNZ,
+               "table too large for a specialised kernel (at most %zu unique rows, %zu entries)", CCSR_JIT_MAX_ROWS, CCSR_JIT_MAX_NNZ);
+    std::vector<int> hrow(row, row + m + 1), hcol(col, col + row[m]);
+    std::vector<double> hval((size_t)row[m]);
+    for (int j = 0; j < row[m]; ++j) hval[(size_t)j] = val_dtype == VEXB_F64 ? ((const double *)val)[j] : (double)((const float *)val)[j];
+    std::string src = ccsr_jit_source(val_dtype, idx_bytes, hrow, hcol, hval);
+    if (compile) {
+        size_t bytes = 0; std::string log;
+        VEXB_TRY(jit_compile_only(src, &bytes, &log));
+        src += "// NVRTC: ok, cubin " + std::to_string(bytes) + " bytes\n";
+    }
+    if (buf) {
+        VEXB_CHECK(*len > src.size(), "buffer too small (%zu <= %zu)", *len, src.size());
+        memcpy(buf, src.c_str(), src.size() + 1);
+    }
+    *len = src.size() + 1;
+    return VEXB_OK;
 }
