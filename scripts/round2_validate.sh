@@ -1,0 +1,32 @@
+#!/bin/bash
+# Round-2 first GPU call: everything written in round 1 after the GPU budget ran out, in one go (single GPU).
+#   gpurun --timeout 600 -- 'bash scripts/round2_validate.sh'
+set -u
+mkdir -p gpurun_out
+export VEXB_RUN_UNVERIFIED=1
+# 1. NVRTC-specialised CCSR kernel + the skipped two-slice C++ stencil run
+timeout 200 python -m pytest tests/test_gpu_ccsr.py tests/test_gpu_cpp_frontend.py -x -q -k "ccsr or stencil" 2>&1 | tail -25 > gpurun_out/r02_unverified_tests.log
+# 2. the two-slice stencil binary under compute-sanitizer (it stopped after 'two_stencils' in round 1)
+VEXCL_TEST_PARTS=2 timeout 200 compute-sanitizer --tool memcheck tests/cpp/bin/test_stencil 12345 > gpurun_out/r02_stencil_2slices_memcheck.log 2>&1
+# 3. timings: CCSR variants incl. ccsr.jit, stencil throughput (also in bench.py extra.stencil)
+timeout 100 python - > gpurun_out/r02_ccsr_jit_probe.json 2>&1 <<'PY'
+import json, sys
+sys.path.insert(0, ".")
+import vexcl_b200 as vx
+from vexcl_b200 import gen
+from bench import time_loop
+n = 256; N = n ** 3
+ctx = vx.Context([0])
+idx, row, col, val = gen.poisson_ccsr(n)
+A = vx.SpMatCCSR(ctx, N, idx, row, col, val)
+x, y = vx.vector(ctx, N), vx.vector(ctx, N)
+x.assign(vx.ElementIndex() * (1.0 / N) + 0.5); y.assign(0.0)
+out = {}
+for jit in (0, 1):
+    vx.set_param("ccsr.jit", jit)
+    for append in (True, False):
+        ms = time_loop(ctx, lambda: A.apply(x, y, 1.0, append), 40, 3, ctx.finish) / 40
+        out[f"jit={jit},append={append}"] = {"ms": ms, "gbs_compulsory": N * (25 if append else 17) / (ms * 1e-3) / 1e9}
+print(json.dumps(out, indent=1))
+PY
+tail -5 gpurun_out/r02_unverified_tests.log; tail -5 gpurun_out/r02_stencil_2slices_memcheck.log; cat gpurun_out/r02_ccsr_jit_probe.json
