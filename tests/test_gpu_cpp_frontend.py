@@ -39,7 +39,7 @@ def _run_stencil(parts: str, timeout: int):
 
 
 def test_cpp_stencil_single_slice(built):
-    """tests/cpp/test_stencil.cpp (the reference's tests/stencil.cpp) on one slice: 7 cases, 6445 checks."""
+    """tests/cpp/test_stencil.cpp (the cases of the reference's tests/stencil.cpp) on one slice."""
     _run_stencil("1", 300)
 
 
