@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 export VEXB_RUN_UNVERIFIED=1
 # 1. NVRTC-specialised CCSR kernel + the skipped two-slice C++ stencil run
-timeout 200 python -m pytest tests/test_gpu_ccsr.py tests/test_gpu_cpp_frontend.py -x -q -k "ccsr or stencil" 2>&1 | tail -25 > gpurun_out/r02_unverified_tests.log
+timeout 300 python -m pytest tests/test_gpu_unverified.py tests/test_gpu_ccsr.py tests/test_gpu_cpp_frontend.py -q -k "unverified or ccsr or stencil or scalar" 2>&1 | tail -25 > gpurun_out/r02_unverified_tests.log
 # 2. the two-slice stencil binary under compute-sanitizer (it stopped after 'two_stencils' in round 1)
 VEXCL_TEST_PARTS=2 timeout 200 compute-sanitizer --tool memcheck tests/cpp/bin/test_stencil 12345 > gpurun_out/r02_stencil_2slices_memcheck.log 2>&1
 # 3. timings: CCSR variants incl. ccsr.jit, stencil throughput (also in bench.py extra.stencil)
@@ -27,6 +27,18 @@ for jit in (0, 1):
     for append in (True, False):
         ms = time_loop(ctx, lambda: A.apply(x, y, 1.0, append), 40, 3, ctx.finish) / 40
         out[f"jit={jit},append={append}"] = {"ms": ms, "gbs_compulsory": N * (25 if append else 17) / (ms * 1e-3) / 1e9}
+# CSR variants on config 3 (2-D Poisson 3162^2): TMA tiles (0) vs thread per row (3)
+row, col, val = gen.poisson_strip(2, 3162)
+Nc = row.size - 1
+Ac = vx.SpMat(ctx, Nc, Nc, row, col, val, vx.FMT_CSR)
+xc, yc = vx.vector(ctx, Nc), vx.vector(ctx, Nc)
+xc.assign(vx.ElementIndex() * (1.0 / Nc) + 0.5)
+nbytes = gen.spmv_bytes(Nc, Nc, int(row[-1]))
+for k in (0, 3):
+    vx.set_param("spmv.kernel", k)
+    ms = time_loop(ctx, lambda: Ac.apply(xc, yc, 1.0, False), 40, 3, ctx.finish) / 40
+    out[f"csr spmv.kernel={k}"] = {"ms": ms, "gbs": nbytes / (ms * 1e-3) / 1e9}
+vx.set_param("spmv.kernel", 0)
 print(json.dumps(out, indent=1))
 PY
 tail -5 gpurun_out/r02_unverified_tests.log; tail -5 gpurun_out/r02_stencil_2slices_memcheck.log; cat gpurun_out/r02_ccsr_jit_probe.json

@@ -437,6 +437,31 @@ __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w
     store_y<T>(y, row_ids ? (size_t)row_ids[i] : i, sum, alpha, append);
 }
 
+// spmv.kernel = 3: one thread per row straight from the CSR arrays ("CSR-scalar").  Neighbouring lanes read
+// neighbouring rows, i.e. addresses a row length apart: not coalesced per instruction, but every 32-byte sector a warp
+// touches is consumed completely by it over the row loop, so with L1 allocation (plain loads, no streaming hint) DRAM
+// traffic stays at the algorithmic figure.  No shared memory, no barrier, no tile descriptor: every thread always has
+// loads in flight, like hell_kernel.  Opt-in (written after the round-1 GPU budget was spent; not yet measured).
+template <class T>
+__global__ void __launch_bounds__(256) csr_scalar_kernel(size_t n, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                                          const T *__restrict__ val, const T *__restrict__ x, T *y, T alpha,
+                                                          int append, const int *__restrict__ row_ids) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int j = rowptr[r];
+    const int e = rowptr[r + 1];
+    T sum = T(0);
+    for (; j + 4 <= e; j += 4) {                                       // four gathers in flight, products in storage order
+        const int c0 = col[j], c1 = col[j + 1], c2 = col[j + 2], c3 = col[j + 3];
+        const T v0 = val[j], v1 = val[j + 1], v2 = val[j + 2], v3 = val[j + 3];
+        const T x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+        sum = t_add<T>(sum, t_mul<T>(v0, x0)); sum = t_add<T>(sum, t_mul<T>(v1, x1));
+        sum = t_add<T>(sum, t_mul<T>(v2, x2)); sum = t_add<T>(sum, t_mul<T>(v3, x3));
+    }
+    for (; j < e; ++j) sum = t_add<T>(sum, t_mul<T>(val[j], __ldg(x + col[j])));
+    store_y<T>(y, row_ids ? (size_t)row_ids[r] : r, sum, alpha, append);
+}
+
 template <class T>
 __global__ void zero_rows_kernel(T *y, size_t n, const int *__restrict__ row_ids) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -544,9 +569,12 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
         if (!append) { zero_rows_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, n, A->row_ids); VEXB_LAUNCHED(); }
         return VEXB_OK;
     }
-    // spmv.kernel: 0 = TMA-staged one-shot tiles, 1 = persistent TMA pipeline, 2 = register-staged tiles
+    // spmv.kernel: 0 = TMA-staged one-shot tiles, 1 = persistent TMA pipeline, 2 = register-staged tiles, 3 = thread per row
     const long variant = param("spmv.kernel", param("spmv.pipeline", 0) ? 1 : 0);
-    if (A->fmt == VEXB_FMT_CSR && variant == 2 && A->tile_nnz <= (size_t)kDirectThreads * kDirectPerThread) {
+    if (A->fmt == VEXB_FMT_CSR && variant == 3) {
+        csr_scalar_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, A->rowptr, A->col, (const T *)A->val, x, y, alpha, append, A->row_ids);
+        VEXB_LAUNCHED();
+    } else if (A->fmt == VEXB_FMT_CSR && variant == 2 && A->tile_nnz <= (size_t)kDirectThreads * kDirectPerThread) {
         const size_t smem = std::max<size_t>(A->tile_nnz, 64) * sizeof(T);
         csr_direct_kernel<T><<<(unsigned)A->n_tiles, kDirectThreads, smem, st>>>(A->tile, A->rowptr, A->col, (const T *)A->val, x, y,
                                                                                 alpha, append, A->row_ids);
