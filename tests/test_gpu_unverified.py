@@ -48,3 +48,31 @@ def test_csr_scalar_kernel_single_precision(scalar_csr, ctx1):
     y.assign(A * x)
     want = oracle.csr_spmv(row, col, val.astype(np.float32).astype(np.float64), xh.astype(np.float64))
     assert np.allclose(y.read(), want, rtol=2e-5, atol=1e-5)
+
+
+@pytest.fixture
+def col16(built):
+    vx.set_param("spmv.col16", 1)                        # hybrid ELL with 16-bit column offsets (read at construction)
+    yield
+    vx.set_param("spmv.col16", 0)
+
+
+@pytest.mark.parametrize("nparts", [1, 2, 3])
+def test_hell_with_16_bit_columns_matches_the_oracle(col16, ctx1, ctx2, ctx3, nparts):
+    ctx = {1: ctx1, 2: ctx2, 3: ctx3}[nparts]
+    cases = [oracle.poisson(2, 200), oracle.poisson(3, 24), oracle.tridiagonal(5000),
+             oracle.random_matrix(4000, 4000, 16, seed=6),             # band too wide in places: falls back to 32-bit
+             oracle.random_matrix(70000, 70000, 8, seed=7)]            # columns further than 32767 from the diagonal: 32-bit
+    for row, col, val in cases:
+        n = row.size - 1
+        xh = oracle.uniform_real(11, n)
+        A = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_HELL)
+        x, y = vx.vector(ctx, xh), vx.vector(ctx, n)
+        y.assign(A * x)
+        want = oracle.csr_spmv(row, col, val, xh)
+        if nparts == 1:
+            assert np.array_equal(y.read(), want)        # only the index encoding changes: same bits as 32-bit columns
+        else:
+            assert np.all(np.abs(y.read() - want) <= 1e-10 * oracle.csr_absrow(row, col, val, xh))
+        y += 3.0 * (A * x)
+        assert np.all(np.abs(y.read() - 4.0 * want) <= 1e-10 * 4 * oracle.csr_absrow(row, col, val, xh))

@@ -14,6 +14,7 @@ struct vexb_spmat {
     // HELL
     size_t ell_width = 0, ell_pitch = 0, tail_nnz = 0;
     int *ell_col = nullptr; void *ell_val = nullptr;
+    short *ell_col16 = nullptr; int ell_shift = 0;   // optional: columns as 16-bit offsets from (row + ell_shift); see spmv.col16
     int *tail_ptr = nullptr; int *tail_col = nullptr; void *tail_val = nullptr;
     int *row_ids = nullptr;        // optional: compressed rows, y index of stored row r (remote strips)
     size_t y_offset = 0;           // y index of stored row 0 when the strip covers a contiguous row range

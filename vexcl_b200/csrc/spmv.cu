@@ -61,6 +61,13 @@ __device__ __forceinline__ float ldg_keep(const float *p, uint64_t policy) {
 __device__ __forceinline__ int ldg_stream(const int *p, uint64_t policy) {
     int v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy)); return v;
 }
+__device__ __forceinline__ short ldg_stream(const short *p, uint64_t policy) {
+    short v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(policy)); return v;
+}
+// Column of an ELL slot.  32-bit storage holds it directly (-1 = padding); 16-bit storage (spmv.col16) holds its
+// distance from (row + shift), with -32768 = padding: 2 bytes less HBM traffic per stored entry for banded matrices.
+__device__ __forceinline__ int ell_column(int raw, size_t, int) { return raw; }
+__device__ __forceinline__ int ell_column(short raw, size_t row, int shift) { return raw == (short)-32768 ? -1 : (int)row + shift + (int)raw; }
 __device__ __forceinline__ double ldg_stream(const double *p, uint64_t policy) {
     double v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy)); return v;
 }
@@ -404,8 +411,8 @@ __global__ void __launch_bounds__(kPipeThreads) csr_pipe_kernel(const int2 *__re
     }
 }
 
-template <class T, int W>
-__global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w_dyn, const int *__restrict__ ell_col,
+template <class T, int W, class C>
+__global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w_dyn, const C *__restrict__ ell_col, int shift,
                                                     const T *__restrict__ ell_val, const int *__restrict__ tail_ptr,
                                                     const int *__restrict__ tail_col, const T *__restrict__ tail_val,
                                                     const T *__restrict__ x, T *y, T alpha, int append,
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w
     if (W > 0) {
         int c[W > 0 ? W : 1]; T v[W > 0 ? W : 1]; T xv[W > 0 ? W : 1];
 #pragma unroll
-        for (int j = 0; j < W; ++j) { c[j] = ldg_stream(ell_col + i + (size_t)j * pitch, stream); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
+        for (int j = 0; j < W; ++j) { c[j] = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
 #pragma unroll
         for (int j = 0; j < W; ++j) xv[j] = (c[j] != -1) ? ldg_keep(x + c[j], keep) : T(0);
 #pragma unroll
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w
         // (4.2 vs 3.3 TB/s effective at average width 12): occupancy hides the latency, and a padded slot
         // (column -1) costs 4 bytes, not 12, because its value is never fetched.
         for (int j = 0; j < w_dyn; ++j) {
-            const int c = ldg_stream(ell_col + i + (size_t)j * pitch, stream);
+            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift);
             if (c != -1) sum = t_add<T>(sum, t_mul<T>(ldg_stream(ell_val + i + (size_t)j * pitch, stream), ldg_keep(x + c, keep)));
         }
     }
@@ -548,6 +555,29 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
         A->tail_nnz = tcol.size();
         VEXB_TRY(upload(ecol, 0, (void **)&A->ell_col, &A->device_bytes));
         VEXB_TRY(upload(eval, 0, &A->ell_val, &A->device_bytes));
+        if (param("spmv.col16", 0) && w > 0) {
+            // Banded matrices: every stored column lies within +-32767 of (row + shift) for one shift per strip, so
+            // the ELL columns fit 16 bits.  The kernel then streams 10 instead of 12 bytes per stored entry.
+            long long lo = 0, hi = 0; bool any = false;
+            for (size_t k = 0; k < w; ++k)
+                for (size_t i = 0; i < n; ++i) {
+                    const int c = ecol[i + pitch * k];
+                    if (c < 0) continue;
+                    const long long d = (long long)c - (long long)i;
+                    if (!any) { lo = hi = d; any = true; } else { lo = std::min(lo, d); hi = std::max(hi, d); }
+                }
+            if (any && hi - lo <= 65534) {
+                const long long shift = lo + 32767;
+                std::vector<short> e16(pitch * w, (short)-32768);
+                for (size_t k = 0; k < w; ++k)
+                    for (size_t i = 0; i < n; ++i) {
+                        const int c = ecol[i + pitch * k];
+                        if (c >= 0) e16[i + pitch * k] = (short)((long long)c - (long long)i - shift);
+                    }
+                A->ell_shift = (int)shift;
+                VEXB_TRY(upload(e16, 0, (void **)&A->ell_col16, &A->device_bytes));
+            }
+        }
         if (A->tail_nnz) {
             VEXB_TRY(upload(tptr, 0, (void **)&A->tail_ptr, &A->device_bytes));
             VEXB_TRY(upload(tcol, 0, (void **)&A->tail_col, &A->device_bytes));
@@ -616,8 +646,11 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
         VEXB_LAUNCHED();
     } else {
         const unsigned blocks = (unsigned)((n + 255) / 256);
-#define HL(W) hell_kernel<T, W><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col, (const T *)A->ell_val, \
-                  A->tail_ptr, A->tail_col, (const T *)A->tail_val, x, y, alpha, append, A->row_ids)
+#define HL(W) do { \
+            if (A->ell_col16) hell_kernel<T, W, short><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col16, A->ell_shift, \
+                  (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, x, y, alpha, append, A->row_ids); \
+            else hell_kernel<T, W, int><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col, 0, \
+                  (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, x, y, alpha, append, A->row_ids); } while (0)
         switch (A->ell_width) {
             case 1: HL(1); break; case 2: HL(2); break; case 3: HL(3); break; case 4: HL(4); break;
             case 5: HL(5); break; case 6: HL(6); break; case 7: HL(7); break; case 8: HL(8); break;
@@ -688,7 +721,7 @@ extern "C" int vexb_spmat_destroy(vexb_spmat *A) {
     if (!A) return VEXB_OK;
     DeviceGuard g(A->dev);
     cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile);
-    cudaFree(A->row_ids); cudaFree(A->ell_col); cudaFree(A->ell_val); cudaFree(A->tail_ptr); cudaFree(A->tail_col); cudaFree(A->tail_val);
+    cudaFree(A->row_ids); cudaFree(A->ell_col); cudaFree(A->ell_col16); cudaFree(A->ell_val); cudaFree(A->tail_ptr); cudaFree(A->tail_col); cudaFree(A->tail_val);
     delete A;
     return VEXB_OK;
 }
