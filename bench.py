@@ -242,7 +242,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     r0, r1 = int(part[k]), int(part[k + 1])
     row, col, val = gen.poisson_strip(2, nx, ny, r0=r0, r1=r1, index_dtype=np.int64)
     slab_rows, slab_nnz = r1 - r0, int(row[-1])
-    fmt = {"auto": vx.FMT_AUTO, "csr": vx.FMT_CSR, "hell": vx.FMT_HELL}[args.format]
+    fmt = {"auto": vx.FMT_AUTO, "csr": vx.FMT_CSR, "hell": vx.FMT_HELL, "patterns": vx.FMT_PATTERNS}[args.format]
     A = vx.SpMat(ctx, N, N, row, col, val, fmt, strip=True)
     info = A.info()
     A_alt = None
@@ -309,12 +309,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     kern_bytes = gen.spmv_bytes(slab_rows, slab_rows, int(loc.nnz))
     achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
     is_hell = loc.fmt == vx.FMT_HELL
-    kname = f"hell_kernel<double,{int(loc.ell_width)}>" if is_hell else "csr_stream_kernel<double>"
+    is_patterns = loc.fmt == vx.FMT_PATTERNS
+    kname = (f"hell_kernel<double,{int(loc.ell_width)}>" if is_hell else
+             f"ccsr_kernel<double> ({int(loc.n_tiles)} row patterns)" if is_patterns else "csr_stream_kernel<double>")
     traffic = None
     tp = ROOT / "profiles" / "roofline_traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("hell_kernel_bytes_per_launch" if is_hell else "csr_stream_kernel_bytes_per_launch")
+            traffic = json.loads(tp.read_text()).get("hell_kernel_bytes_per_launch" if is_hell else
+                                                     "ccsr_kernel_bytes_per_launch" if is_patterns else "csr_stream_kernel_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -425,6 +428,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "algorithmic_bytes_per_step": step_bytes,
                        "format": (f"CSR in; device format chosen by SpMat (as the reference does, spmat.hpp:92-103): hybrid ELL width "
                                   f"{int(loc.ell_width)}, CSR tail {int(loc.csr_tail_nnz)} nnz, 32-bit columns" if is_hell else
+                                  f"CSR in; device format: {int(loc.n_tiles)} unique row patterns + one pattern id per row "
+                                  f"(VEXB_FMT_PATTERNS, requested explicitly)" if is_patterns else
                                   f"CSR in; device format: CSR row-block stream (TMA-staged tiles of {int(loc.tile_nnz)} nnz), 32-bit indices"),
                        "requested_format": args.format,
                        "cache": "inputs larger than L2 (0.8 GB per GPU vs 126 MB L2)", "partition": "equal weights"},
@@ -561,7 +566,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cg", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="combine reductions with ncclAllReduce instead of the fused peer-memory exchange")
-    ap.add_argument("--format", default="auto", choices=["auto", "csr", "hell"])
+    ap.add_argument("--format", default="auto", choices=["auto", "csr", "hell", "patterns"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -345,8 +345,16 @@ typedef struct vexb_spmat vexb_spmat;
 typedef enum {
     VEXB_FMT_AUTO = 0,  /* CSR row-block stream kernel unless ELL is clearly better */
     VEXB_FMT_CSR = 1,   /* row-block CSR, tiles staged through shared memory by TMA bulk copies */
-    VEXB_FMT_HELL = 2   /* hybrid ELL + CSR tail, width by hybrid_ell.inl:66-114 */
+    VEXB_FMT_HELL = 2,  /* hybrid ELL + CSR tail, width by hybrid_ell.inl:66-114 */
+    VEXB_FMT_PATTERNS = 3 /* the strip's unique rows (column offsets from the diagonal + values) and one pattern id per
+                             row: the reference's CCSR (spmat/ccsr.hpp) found automatically.  Used when the strip has at
+                             most "spmv.max_patterns" (256) distinct rows and no row map; otherwise as VEXB_FMT_AUTO.
+                             Opt-in in round 1 (not yet run on a GPU). */
 } vexb_spfmt;
+/* Host-only: the row patterns VEXB_FMT_PATTERNS would use.  *n_patterns = number of distinct rows; idx (optional,
+ * nrows entries) = pattern of each row.  Returns VEXB_ERR_UNSUPPORTED when there are more than max_patterns. */
+int vexb_csr_row_patterns(size_t nrows, const void *ptr, int ptr_bytes, const void *col, int col_bytes,
+                          const void *val, int val_dtype, size_t max_patterns, size_t *n_patterns, int32_t *idx);
 
 int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols,
                     const void *ptr, int ptr_bytes, const void *col, int col_bytes,
@@ -354,10 +362,10 @@ int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols,
 int vexb_spmat_destroy(vexb_spmat *A);
 typedef struct {
     size_t  nrows, ncols, nnz;
-    int32_t fmt;          /* VEXB_FMT_CSR or VEXB_FMT_HELL */
+    int32_t fmt;          /* VEXB_FMT_CSR, VEXB_FMT_HELL or VEXB_FMT_PATTERNS */
     int32_t val_dtype;
     size_t  ell_width, ell_pitch, csr_tail_nnz;   /* HELL only */
-    size_t  n_tiles, tile_nnz;                    /* CSR only  */
+    size_t  n_tiles, tile_nnz;                    /* CSR: tiles, nnz per tile; PATTERNS: unique rows, entries in their table */
     size_t  device_bytes;                         /* bytes of matrix data resident in HBM */
 } vexb_spmat_info;
 int vexb_spmat_get_info(const vexb_spmat *A, vexb_spmat_info *info);

@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 export VEXB_RUN_UNVERIFIED=1
 # 1. NVRTC-specialised CCSR kernel + the skipped two-slice C++ stencil run
-timeout 300 python -m pytest tests/test_gpu_unverified.py tests/test_gpu_ccsr.py tests/test_gpu_cpp_frontend.py -q -k "unverified or ccsr or stencil or scalar or 16_bit" 2>&1 | tail -25 > gpurun_out/r02_unverified_tests.log
+timeout 300 python -m pytest tests/test_gpu_unverified.py tests/test_gpu_ccsr.py tests/test_gpu_cpp_frontend.py -q -k "unverified or ccsr or stencil or scalar or 16_bit or pattern" 2>&1 | tail -25 > gpurun_out/r02_unverified_tests.log
 # 2. the two-slice stencil binary under compute-sanitizer (it stopped after 'two_stencils' in round 1)
 VEXCL_TEST_PARTS=2 timeout 200 compute-sanitizer --tool memcheck tests/cpp/bin/test_stencil 12345 > gpurun_out/r02_stencil_2slices_memcheck.log 2>&1
 # 3. timings: CCSR variants incl. ccsr.jit, stencil throughput (also in bench.py extra.stencil)
@@ -47,6 +47,13 @@ for c16 in (0, 1):
     out[f"hell spmv.col16={c16}"] = {"ms": ms, "gbs": nbytes / (ms * 1e-3) / 1e9}
     del Ah
 vx.set_param("spmv.col16", 0)
+# row-pattern strip (VEXB_FMT_PATTERNS -> ccsr_kernel), generic and NVRTC-specialised
+Ap = vx.SpMat(ctx, Nc, Nc, row, col, val, vx.FMT_PATTERNS)
+for jit in (0, 1):
+    vx.set_param("ccsr.jit", jit)
+    ms = time_loop(ctx, lambda: Ap.apply(xc, yc, 1.0, False), 100, 5, ctx.finish) / 100
+    out[f"patterns ccsr.jit={jit}"] = {"ms": ms, "gbs_effective": nbytes / (ms * 1e-3) / 1e9, "patterns": int(Ap.info().loc.n_tiles)}
+vx.set_param("ccsr.jit", 0)
 print(json.dumps(out, indent=1))
 PY
 tail -5 gpurun_out/r02_unverified_tests.log; tail -5 gpurun_out/r02_stencil_2slices_memcheck.log; cat gpurun_out/r02_ccsr_jit_probe.json

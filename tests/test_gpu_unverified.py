@@ -76,3 +76,26 @@ def test_hell_with_16_bit_columns_matches_the_oracle(col16, ctx1, ctx2, ctx3, np
             assert np.all(np.abs(y.read() - want) <= 1e-10 * oracle.csr_absrow(row, col, val, xh))
         y += 3.0 * (A * x)
         assert np.all(np.abs(y.read() - 4.0 * want) <= 1e-10 * 4 * oracle.csr_absrow(row, col, val, xh))
+
+
+@pytest.mark.parametrize("nparts", [1, 2, 3])
+def test_row_pattern_strips_match_the_oracle(built, ctx1, ctx2, ctx3, nparts):
+    """VEXB_FMT_PATTERNS: strips with few distinct rows are multiplied by the CCSR kernel (same bits as ELL / CSR)."""
+    ctx = {1: ctx1, 2: ctx2, 3: ctx3}[nparts]
+    for (row, col, val), compressible in ((oracle.poisson(2, 200), True), (oracle.poisson(3, 24), True),
+                                          (oracle.tridiagonal(5000), True), (oracle.random_matrix(3000, 3000, 8, seed=2), False)):
+        n = row.size - 1
+        xh = oracle.uniform_real(12, n)
+        A = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_PATTERNS)
+        assert (A.info().loc.fmt == vx.FMT_PATTERNS) == compressible
+        if compressible:
+            assert A.info().loc.n_tiles <= 3
+        x, y = vx.vector(ctx, xh), vx.vector(ctx, n)
+        y.assign(A * x)
+        want = oracle.csr_spmv(row, col, val, xh)
+        if nparts == 1:
+            assert np.array_equal(y.read(), want)
+        else:
+            assert np.all(np.abs(y.read() - want) <= 1e-10 * oracle.csr_absrow(row, col, val, xh))
+        y -= 0.5 * (A * x)
+        assert np.all(np.abs(y.read() - 0.5 * want) <= 1e-10 * oracle.csr_absrow(row, col, val, xh))

@@ -16,7 +16,7 @@ F64, F32, I32, U32, I64, U64 = range(6)
 SET, ADD, SUB, MUL, DIV, MOD, AND, OR, XOR, LSH, RSH = range(11)
 SUM, SUM_KAHAN, MAX, MIN, MINMAX = range(5)
 TERM_VEC, TERM_SCALAR, TERM_INDEX, TERM_DSCALAR = range(4)
-FMT_AUTO, FMT_CSR, FMT_HELL = range(3)
+FMT_AUTO, FMT_CSR, FMT_HELL, FMT_PATTERNS = range(4)
 MAX_TERMS, MAX_CODE, MAX_STACK = 16, 64, 12
 
 _OPS = ("TERM CVT NEG LNOT ADD SUB MUL DIV MOD BAND BOR BXOR SHL SHR LT GT LE GE EQ NE LAND LOR SELECT "
@@ -142,6 +142,7 @@ def lib():
         "vexb_halo_plan_counts": ([vp, i, P(sz), P(sz)], i),
         "vexb_halo_plan_send_cols": ([vp, i, vp], i),
         "vexb_csr_create": ([i, vp, sz, sz, vp, i, vp, i, vp, i, i, P(vp)], i),
+        "vexb_csr_row_patterns": ([sz, vp, i, vp, i, vp, i, sz, P(sz), vp], i),
         "vexb_spmat_destroy": ([vp], i),
         "vexb_spmat_get_info": ([vp, P(SpmatInfo)], i),
         "vexb_spmat_hell_download": ([vp, vp, vp, vp, vp, vp], i),

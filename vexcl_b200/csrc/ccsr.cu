@@ -17,6 +17,7 @@
 #include <vector>
 #include "common.cuh"
 #include "jit.hpp"
+#include "ccsr.hpp"
 
 struct vexb_ccsr {
     int dev = 0, val_dtype = VEXB_F64, idx_bytes = 1;
@@ -264,6 +265,14 @@ extern "C" int vexb_ccsr_create(int dev, void *stream, size_t n, size_t m, const
                                 const void *row, int row_bytes, const void *col, int col_bytes,
                                 const void *val, int val_dtype, vexb_ccsr **out) {
     (void)stream;
+    return vexb::ccsr_create_ex(dev, n, n, m, idx, idx_bytes, row, row_bytes, col, col_bytes, val, val_dtype, out);
+}
+
+// n rows applied to a vector of xlen elements (xlen = n for vex::SpMatCCSR; a row strip of vex::SpMat stored as row
+// patterns, spmv.cu, has xlen = the strip's local column count).
+int vexb::ccsr_create_ex(int dev, size_t n, size_t xlen, size_t m, const void *idx, int idx_bytes,
+                         const void *row, int row_bytes, const void *col, int col_bytes,
+                         const void *val, int val_dtype, vexb_ccsr **out) {
     VEXB_CHECK(out, "null output handle");
     VEXB_CHECK((idx || !n) && row && (idx_bytes == 4 || idx_bytes == 8) && (row_bytes == 4 || row_bytes == 8) && (col_bytes == 4 || col_bytes == 8),
                "idx/row/col must be 32- or 64-bit integer arrays");
@@ -298,7 +307,7 @@ extern "C" int vexb_ccsr_create(int dev, void *stream, size_t n, size_t m, const
         const long long u = read_int(idx, idx_bytes, false, i);
         if (!(u >= 0 && (size_t)u < m)) { delete A; VEXB_FAIL(VEXB_ERR_INVALID, "CCSR idx[%zu] = %lld names no unique row (m = %zu)", i, u, m); }
         // the reference reads x[i + col[j]] unchecked (ccsr.hpp:195); a matrix that reaches outside x is rejected here
-        if ((long long)i + lo[(size_t)u] < 0 || (long long)i + hi[(size_t)u] >= (long long)n) {
+        if ((long long)i + lo[(size_t)u] < 0 || (long long)i + hi[(size_t)u] >= (long long)xlen) {
             delete A; VEXB_FAIL(VEXB_ERR_INVALID, "CCSR row %zu (unique row %lld) reaches outside the vector", i, u);
         }
         if (A->idx_bytes == 1) i8[i] = (uint8_t)u; else if (A->idx_bytes == 2) i16[i] = (uint16_t)u; else i32[i] = (int32_t)u;

@@ -16,6 +16,8 @@ struct vexb_spmat {
     int *ell_col = nullptr; void *ell_val = nullptr;
     short *ell_col16 = nullptr; int ell_shift = 0;   // optional: columns as 16-bit offsets from (row + ell_shift); see spmv.col16
     int *tail_ptr = nullptr; int *tail_col = nullptr; void *tail_val = nullptr;
+    vexb_ccsr *patterns = nullptr; // VEXB_FMT_PATTERNS: the strip as unique row patterns + one pattern id per row (csrc/ccsr.cu)
+    size_t n_patterns = 0;
     int *row_ids = nullptr;        // optional: compressed rows, y index of stored row r (remote strips)
     size_t y_offset = 0;           // y index of stored row 0 when the strip covers a contiguous row range
     size_t nrows_stored = 0;       // rows held in the arrays (== nrows unless row_ids)

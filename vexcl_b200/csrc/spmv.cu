@@ -23,6 +23,10 @@
 // sentinel column -1, CSR tail; hybrid_ell.inl:60,139-144,252-268) with 32-bit
 // columns, and unrolls the ELL loop for the common small widths.
 #include "spmat.hpp"
+#include "ccsr.hpp"
+#include <cstring>
+#include <string>
+#include <unordered_map>
 #include <algorithm>
 
 
@@ -502,9 +506,64 @@ static size_t hell_width(const std::vector<int> &rowptr, size_t n) {
     return maxw;
 }
 
+// Row patterns: many PDE matrices repeat a handful of rows (same column offsets from the diagonal, same values).  Such
+// a strip is stored as the unique rows plus ONE BYTE per row naming its pattern -- the reference's CCSR format
+// (spmat/ccsr.hpp), found automatically -- and multiplied by ccsr_kernel: 17 B/row of compulsory traffic for a 5-point
+// stencil instead of 76 B/row in hybrid ELL.  Values are compared bit for bit and rows are accumulated in storage
+// order, so the product has the same bits as the ELL / CSR kernels.  Returns false when the strip has more than
+// `max_patterns` distinct rows.
 template <class T>
-static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col, std::vector<T> &val, int fmt) {
+static bool find_row_patterns(size_t n, const std::vector<int> &rowptr, const std::vector<int> &col, const std::vector<T> &val,
+                              size_t max_patterns, std::vector<int> &idx, std::vector<int> &prow, std::vector<int> &pcol,
+                              std::vector<T> &pval) {
+    idx.assign(n, 0); prow.assign(1, 0); pcol.clear(); pval.clear();
+    std::unordered_map<std::string, int> seen;
+    std::string key;
+    int last = -1;
+    for (size_t i = 0; i < n; ++i) {
+        const int b = rowptr[i], w = rowptr[i + 1] - b;
+        if (last >= 0 && prow[last + 1] - prow[last] == w) {           // most rows repeat the previous row's pattern
+            const int q = prow[last];
+            bool same = true;
+            for (int j = 0; j < w && same; ++j)
+                same = (col[b + j] - (int)i == pcol[q + j]) && std::memcmp(&val[b + j], &pval[q + j], sizeof(T)) == 0;
+            if (same) { idx[i] = last; continue; }
+        }
+        key.resize((size_t)w * (sizeof(int) + sizeof(T)));
+        for (int j = 0; j < w; ++j) {
+            const int rel = col[b + j] - (int)i;
+            std::memcpy(&key[(size_t)j * sizeof(int)], &rel, sizeof(int));
+            std::memcpy(&key[(size_t)w * sizeof(int) + (size_t)j * sizeof(T)], &val[b + j], sizeof(T));
+        }
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+            if (prow.size() - 1 >= max_patterns) return false;
+            const int id = (int)prow.size() - 1;
+            for (int j = 0; j < w; ++j) { pcol.push_back(col[b + j] - (int)i); pval.push_back(val[b + j]); }
+            prow.push_back((int)pcol.size());
+            it = seen.emplace(key, id).first;
+        }
+        idx[i] = last = it->second;
+    }
+    return true;
+}
+
+template <class T>
+static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col, std::vector<T> &val, int fmt, bool plain) {
     const size_t n = A->nrows_stored;
+    if (fmt == VEXB_FMT_PATTERNS) {
+        // only for strips whose stored row r is row r of y (no row map) and that are worth it; otherwise as AUTO
+        std::vector<int> idx, prow, pcol; std::vector<T> pval;
+        const size_t limit = (size_t)std::max(1l, std::min(param("spmv.max_patterns", 256), 65536l));
+        if (plain && n > 0 && A->nnz > 0 && find_row_patterns<T>(n, rowptr, col, val, limit, idx, prow, pcol, pval)) {
+            A->fmt = VEXB_FMT_PATTERNS;
+            A->n_patterns = prow.size() - 1;
+            VEXB_TRY(ccsr_create_ex(A->dev, n, A->ncols, A->n_patterns, idx.data(), 4, prow.data(), 4, pcol.data(), 4, pval.data(),
+                                    A->val_dtype, &A->patterns));
+            return VEXB_OK;
+        }
+        fmt = VEXB_FMT_AUTO;
+    }
     if (fmt == VEXB_FMT_AUTO) {
         // As the reference does on GPUs (spmat.hpp:98-103): hybrid ELL.  Measured on B200 it beats the CSR
         // stream kernel even with 40 % padding (profiles/r01_tune_spmv_variants.jsonl); only when the
@@ -599,6 +658,7 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
         if (!append) { zero_rows_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, n, A->row_ids); VEXB_LAUNCHED(); }
         return VEXB_OK;
     }
+    if (A->fmt == VEXB_FMT_PATTERNS) return vexb_ccsr_spmv(A->dev, (void *)st, A->patterns, x, y, (double)alpha, append);
     // spmv.kernel: 0 = TMA-staged one-shot tiles, 1 = persistent TMA pipeline, 2 = register-staged tiles, 3 = thread per row
     const long variant = param("spmv.kernel", param("spmv.pipeline", 0) ? 1 : 0);
     if (A->fmt == VEXB_FMT_CSR && variant == 3) {
@@ -673,8 +733,8 @@ int vexb::spmat_from_csr(int dev, size_t nrows, size_t ncols, std::vector<int> &
     A->nrows_stored = rowptr.size() - 1; A->nnz = (size_t)rowptr.back();
     const size_t nnz = A->nnz;
     int st = VEXB_OK;
-    if (val_dtype == VEXB_F64) { std::vector<double> v((const double *)val, (const double *)val + nnz); st = build<double>(A, rowptr, col, v, fmt); }
-    else { std::vector<float> v((const float *)val, (const float *)val + nnz); st = build<float>(A, rowptr, col, v, fmt); }
+    if (val_dtype == VEXB_F64) { std::vector<double> v((const double *)val, (const double *)val + nnz); st = build<double>(A, rowptr, col, v, fmt, row_ids == nullptr); }
+    else { std::vector<float> v((const float *)val, (const float *)val + nnz); st = build<float>(A, rowptr, col, v, fmt, row_ids == nullptr); }
     if (st == VEXB_OK && row_ids) {
         std::vector<int> ids(*row_ids);
         st = upload(ids, 0, (void **)&A->row_ids, &A->device_bytes);
@@ -694,7 +754,7 @@ extern "C" int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols
     VEXB_CHECK(ptr_bytes == 4 || ptr_bytes == 8, "ptr_bytes must be 4 or 8");
     VEXB_CHECK(col_bytes == 4 || col_bytes == 8, "col_bytes must be 4 or 8");
     VEXB_CHECK(val_dtype == VEXB_F64 || val_dtype == VEXB_F32, "values must be f64 or f32");
-    VEXB_CHECK(fmt >= VEXB_FMT_AUTO && fmt <= VEXB_FMT_HELL, "bad format %d", fmt);
+    VEXB_CHECK(fmt >= VEXB_FMT_AUTO && fmt <= VEXB_FMT_PATTERNS, "bad format %d", fmt);
     VEXB_CHECK(nrows == 0 || ptr, "ptr is NULL");
     VEXB_CHECK(nrows < (size_t)INT32_MAX && ncols < (size_t)INT32_MAX, "strip dimensions exceed 32-bit local indices");
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
@@ -721,6 +781,7 @@ extern "C" int vexb_spmat_destroy(vexb_spmat *A) {
     if (!A) return VEXB_OK;
     DeviceGuard g(A->dev);
     cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile);
+    vexb_ccsr_destroy(A->patterns);
     cudaFree(A->row_ids); cudaFree(A->ell_col); cudaFree(A->ell_col16); cudaFree(A->ell_val); cudaFree(A->tail_ptr); cudaFree(A->tail_col); cudaFree(A->tail_val);
     delete A;
     return VEXB_OK;
@@ -734,7 +795,39 @@ extern "C" int vexb_spmat_get_info(const vexb_spmat *A, vexb_spmat_info *info) {
     info->ell_width = A->ell_width; info->ell_pitch = A->ell_pitch; info->csr_tail_nnz = A->tail_nnz;
     info->n_tiles = A->n_tiles; info->tile_nnz = A->tile_nnz;
     info->device_bytes = A->device_bytes;
+    if (A->patterns) {
+        vexb_ccsr_info ci;
+        VEXB_TRY(vexb_ccsr_get_info(A->patterns, &ci));
+        info->n_tiles = A->n_patterns;                   // PATTERNS: number of unique rows
+        info->tile_nnz = ci.nnz;                         //           entries in the unique-row table
+        info->device_bytes += ci.device_bytes;
+    }
     return VEXB_OK;
+}
+
+extern "C" int vexb_csr_row_patterns(size_t nrows, const void *ptr, int ptr_bytes, const void *col, int col_bytes,
+                                     const void *val, int val_dtype, size_t max_patterns, size_t *n_patterns, int32_t *idx) {
+    VEXB_CHECK(n_patterns && (ptr || !nrows), "null argument");
+    VEXB_CHECK((ptr_bytes == 4 || ptr_bytes == 8) && (col_bytes == 4 || col_bytes == 8), "ptr/col must be 32- or 64-bit integers");
+    VEXB_CHECK(val_dtype == VEXB_F64 || val_dtype == VEXB_F32, "values must be f64 or f32");
+    VEXB_CHECK(nrows < (size_t)INT32_MAX, "too many rows");
+    const int64_t p0 = nrows ? read_index(ptr, ptr_bytes, 0) : 0;
+    const int64_t nnz = nrows ? read_index(ptr, ptr_bytes, nrows) - p0 : 0;
+    VEXB_CHECK(nnz >= 0 && nnz < (int64_t)INT32_MAX, "nnz does not fit 32 bits");
+    std::vector<int> rp(nrows + 1, 0), c((size_t)nnz), id, prow, pcol;
+    for (size_t i = 0; i <= nrows && nrows; ++i) rp[i] = (int)(read_index(ptr, ptr_bytes, i) - p0);
+    for (size_t j = 0; j < (size_t)nnz; ++j) c[j] = (int)read_index(col, col_bytes, j);
+    bool ok;
+    if (val_dtype == VEXB_F64) {
+        std::vector<double> v((const double *)val, (const double *)val + nnz), pv;
+        ok = find_row_patterns<double>(nrows, rp, c, v, max_patterns, id, prow, pcol, pv);
+    } else {
+        std::vector<float> v((const float *)val, (const float *)val + nnz), pv;
+        ok = find_row_patterns<float>(nrows, rp, c, v, max_patterns, id, prow, pcol, pv);
+    }
+    *n_patterns = ok ? prow.size() - 1 : 0;
+    if (ok && idx) std::memcpy(idx, id.data(), nrows * sizeof(int32_t));
+    return ok ? VEXB_OK : VEXB_ERR_UNSUPPORTED;
 }
 
 extern "C" int vexb_spmat_hell_download(const vexb_spmat *A, int32_t *ell_col, void *ell_val,
