@@ -418,6 +418,16 @@ int vexb_stencil_apply(int dev, void *stream, int dtype, const void *s, int widt
                        const void *x, size_t n, const void *left, const void *right,
                        void *y, double alpha, int append);
 int vexb_copy_peer(int dst_dev, void *dst, int src_dev, const void *src, size_t bytes, void *stream);
+/* User-defined stencil operators: vex::StencilOperator / VEX_STENCIL_OPERATOR (stencil.hpp:510-680).
+ *   y[i] (=|+=) alpha * f(X),  X[k] = the element k places from i (k in [-center, width-1-center]); `body` is the C
+ * source of f with X a pointer into the staged window, e.g. "return sin(X[1] - X[0]) + sin(X[0] - X[-1]);".
+ * register() is host-only and returns the same id for the same definition; the kernel is compiled by NVRTC at the first
+ * apply() on a device (needs libnvrtc; there is no pre-compiled alternative).  source() returns the generated kernel
+ * (compile != 0: also runs NVRTC for sm_100a, no device needed).  Opt-in in round 1: not yet run on a GPU. */
+int vexb_stencil_operator_register(int dtype, int width, int center, const char *body, int *id);
+int vexb_stencil_operator_source(int id, char *buf, size_t *len, int compile);
+int vexb_stencil_operator_apply(int dev, void *stream, int id, const void *x, size_t n, const void *left,
+                                const void *right, void *y, double alpha, int append);
 
 /* ------------------------------------------------------------------------
  * Distributed SpMat part: the slice of a vex::SpMat owned by one device

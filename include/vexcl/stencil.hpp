@@ -4,75 +4,43 @@
  * vex::stencil<T> (vexcl/stencil.hpp:168-330): convolution of a vector with a small stencil,
  *     y = x * s;   y += x * s;   y = 42 * (x * s);   y = x * s + x * s;        (also for multivectors)
  *     y[i] = sum_k s[k] * x[clamp(i + k - center, 0, n-1)]
+ * and vex::StencilOperator / VEX_STENCIL_OPERATOR (stencil.hpp:510-680): y = f(X) with a user-supplied body,
+ *     VEX_STENCIL_OPERATOR(oscillate, double, 3, 1, "return sin(X[1] - X[0]) + sin(X[0] - X[-1]);", ctx);
+ *     y = oscillate(x);
  *
- * The product is libvexb200's stencil_kernel (csrc/stencil.cu).  With several device slices the elements a slice
- * needs from its neighbours are copied device to device into a per-slice halo buffer before the launch (the reference
- * stages them through the host, stencil.hpp:86-150); like the reference, the exchange waits for the queues on both
- * sides.  The user-defined StencilOperator (VEX_STENCIL_OPERATOR, stencil.hpp:510-680) is not provided.
+ * The convolution is libvexb200's stencil_kernel (csrc/stencil.cu); a user-defined operator is generated and compiled
+ * by NVRTC at first use, as the reference generates its kernel per operator.  With several device slices the elements
+ * a slice needs from its neighbours are copied device to device into a per-slice halo buffer before the launch (the
+ * reference stages them through the host, stencil.hpp:86-150); like the reference, the exchange waits for the queues
+ * on both sides.
  */
 #include <algorithm>
 #include <initializer_list>
+#include <string>
 #include "vector.hpp"
 #include "multivector.hpp"
 
 namespace vex {
+namespace detail {
 
+/// Halo buffers and their exchange, shared by stencil and StencilOperator (stencil_base, stencil.hpp:43-150).
 template <typename T>
-class stencil {
-    public:
-        typedef T value_type;
-
-        /// queue list, stencil values, index of the center element (stencil.hpp:179-228).
-        stencil(const std::vector<backend::command_queue> &queue, const std::vector<T> &st, unsigned center)
-            : queue(queue) { init(st.data(), st.size(), center); }
-        template <class Iterator>
-        stencil(const std::vector<backend::command_queue> &queue, Iterator begin, Iterator end, unsigned center)
-            : queue(queue) { std::vector<T> st(begin, end); init(st.data(), st.size(), center); }
-        stencil(const std::vector<backend::command_queue> &queue, std::initializer_list<T> list, unsigned center)
-            : queue(queue) { std::vector<T> st(list); init(st.data(), st.size(), center); }
-
-        /// y = alpha * (x * s)  or  y += alpha * (x * s)   (stencil<T>::apply, stencil.hpp:258-330).
-        void apply(const vex::vector<T> &x, vex::vector<T> &y, T alpha = 1, bool append = false) const {
-            precondition(x.size() == y.size(), "stencil: vectors differ in size");
-            precondition(x.nparts() == queue.size() && y.nparts() == queue.size(), "stencil: vectors live on other queues");
-            std::vector<const T*> left(queue.size(), nullptr), right(queue.size(), nullptr);
-            exchange_halos(x, left, right);
-            for (unsigned d = 0; d < queue.size(); ++d)
-                VEXB_CHECKED(vexb_stencil_apply(queue[d].ordinal(), queue[d].raw(), dtype_of<T>::value, s[d].raw(), width, lhalo,
-                                                x(d).raw(), x.part_size(d), left[d], right[d], y(d).raw(),
-                                                static_cast<double>(alpha), append));
-        }
-        unsigned size() const { return static_cast<unsigned>(width); }
-    private:
+class stencil_halos {
+    protected:
         std::vector<backend::command_queue> queue;
-        std::vector<backend::device_vector<T>> s, dbuf;
+        std::vector<backend::device_vector<T>> dbuf;
         int width = 0, lhalo = 0, rhalo = 0;
 
-        void init(const T *st, size_t n, unsigned center) {
+        stencil_halos(const std::vector<backend::command_queue> &q, size_t n, unsigned center) : queue(q) {
             precondition(!queue.empty() && n >= 1 && center < n, "stencil needs width >= 1 and center < width");   // stencil.hpp:70-74
             width = static_cast<int>(n); lhalo = static_cast<int>(center); rhalo = width - lhalo - 1;
-            for (unsigned d = 0; d < queue.size(); ++d) {
-                s.emplace_back(queue[d], n, st);
+            for (unsigned d = 0; d < queue.size(); ++d)
                 dbuf.emplace_back(queue[d], static_cast<size_t>(width));          // one more than needed, never empty (stencil.hpp:81-82)
-            }
-            for (auto &q : queue) q.finish();
         }
 
-        /// Copy global elements [g0, g1) of x into dbuf[d] at element offset `at`.
-        void gather(const vex::vector<T> &x, unsigned d, size_t at, size_t g0, size_t g1) const {
-            for (unsigned p = 0; p < queue.size(); ++p) {
-                const size_t a = std::max(g0, x.part_start(p)), b = std::min(g1, x.part_start(p) + x.part_size(p));
-                if (a < b)
-                    VEXB_CHECKED(vexb_copy_peer(queue[d].ordinal(), dbuf[d].raw_ptr() + at + (a - g0), queue[p].ordinal(),
-                                                x(p).raw_ptr() + (a - x.part_start(p)), (b - a) * sizeof(T), queue[d].raw()));
-            }
-        }
-        void fill(unsigned d, size_t at, size_t count, T value) const {
-            std::vector<T> h(count, value);
-            dbuf[d].write(queue[d], at, count, h.data(), true);
-        }
-
+        /// Fills left[d] / right[d] with the halo pointers of every slice that is not at an end of the vector.
         void exchange_halos(const vex::vector<T> &x, std::vector<const T*> &left, std::vector<const T*> &right) const {
+            precondition(x.nparts() == queue.size(), "stencil: the vector lives on other queues");
             if (queue.size() <= 1 || width <= 1) return;                          // stencil.hpp:89
             const size_t n = x.size();
             for (auto &q : queue) q.finish();                                     // the neighbours' slices must be complete
@@ -94,6 +62,56 @@ class stencil {
             }
             for (auto &q : queue) q.finish();                                     // nobody overwrites x while a neighbour copies from it
         }
+    private:
+        /// Copy global elements [g0, g1) of x into dbuf[d] at element offset `at`.
+        void gather(const vex::vector<T> &x, unsigned d, size_t at, size_t g0, size_t g1) const {
+            for (unsigned p = 0; p < queue.size(); ++p) {
+                const size_t a = std::max(g0, x.part_start(p)), b = std::min(g1, x.part_start(p) + x.part_size(p));
+                if (a < b)
+                    VEXB_CHECKED(vexb_copy_peer(queue[d].ordinal(), dbuf[d].raw_ptr() + at + (a - g0), queue[p].ordinal(),
+                                                x(p).raw_ptr() + (a - x.part_start(p)), (b - a) * sizeof(T), queue[d].raw()));
+            }
+        }
+        void fill(unsigned d, size_t at, size_t count, T value) const {
+            std::vector<T> h(count, value);
+            dbuf[d].write(queue[d], at, count, h.data(), true);
+        }
+};
+
+} // namespace detail
+
+template <typename T>
+class stencil : private detail::stencil_halos<T> {
+        typedef detail::stencil_halos<T> Base;
+    public:
+        typedef T value_type;
+
+        /// queue list, stencil values, index of the center element (stencil.hpp:179-228).
+        stencil(const std::vector<backend::command_queue> &queue, const std::vector<T> &st, unsigned center)
+            : Base(queue, st.size(), center) { init(st.data()); }
+        template <class Iterator>
+        stencil(const std::vector<backend::command_queue> &queue, Iterator begin, Iterator end, unsigned center)
+            : Base(queue, static_cast<size_t>(std::distance(begin, end)), center) { std::vector<T> st(begin, end); init(st.data()); }
+        stencil(const std::vector<backend::command_queue> &queue, std::initializer_list<T> list, unsigned center)
+            : Base(queue, list.size(), center) { std::vector<T> st(list); init(st.data()); }
+
+        /// y = alpha * (x * s)  or  y += alpha * (x * s)   (stencil<T>::apply, stencil.hpp:258-330).
+        void apply(const vex::vector<T> &x, vex::vector<T> &y, T alpha = 1, bool append = false) const {
+            precondition(x.size() == y.size() && y.nparts() == this->queue.size(), "stencil: vectors differ in size or queues");
+            std::vector<const T*> left(this->queue.size(), nullptr), right(this->queue.size(), nullptr);
+            this->exchange_halos(x, left, right);
+            for (unsigned d = 0; d < this->queue.size(); ++d)
+                VEXB_CHECKED(vexb_stencil_apply(this->queue[d].ordinal(), this->queue[d].raw(), dtype_of<T>::value, s[d].raw(),
+                                                this->width, this->lhalo, x(d).raw(), x.part_size(d), left[d], right[d], y(d).raw(),
+                                                static_cast<double>(alpha), append));
+        }
+        unsigned size() const { return static_cast<unsigned>(this->width); }
+    private:
+        std::vector<backend::device_vector<T>> s;
+        void init(const T *st) {
+            for (unsigned d = 0; d < this->queue.size(); ++d) s.emplace_back(this->queue[d], static_cast<size_t>(this->width), st);
+            for (auto &q : this->queue) q.finish();
+        }
 };
 
 template <typename T>
@@ -105,5 +123,45 @@ additive_operator<stencil<T>, multivector<T, N>> operator*(const stencil<T> &s, 
 template <typename T, size_t N>
 additive_operator<stencil<T>, multivector<T, N>> operator*(const multivector<T, N> &x, const stencil<T> &s) { return additive_operator<stencil<T>, multivector<T, N>>(s, x); }
 
+/// User-defined stencil operator; Impl::body() is the C source of `T f(const T *X)` (stencil.hpp:510-545).
+template <typename T, unsigned width, unsigned center, class Impl>
+class StencilOperator : private detail::stencil_halos<T> {
+        typedef detail::stencil_halos<T> Base;
+    public:
+        typedef T value_type;
+        StencilOperator(const std::vector<backend::command_queue> &queue) : Base(queue, width, center), id(-1) {
+            VEXB_CHECKED(vexb_stencil_operator_register(dtype_of<T>::value, width, center, std::string(Impl::body()).c_str(), &id));
+        }
+        additive_operator<StencilOperator, vector<T>> operator()(const vector<T> &x) const {
+            return additive_operator<StencilOperator, vector<T>>(*this, x);
+        }
+        template <size_t N>
+        additive_operator<StencilOperator, multivector<T, N>> operator()(const multivector<T, N> &x) const {
+            return additive_operator<StencilOperator, multivector<T, N>>(*this, x);
+        }
+        /// y = alpha * f(x)  or  y += alpha * f(x)
+        void apply(const vex::vector<T> &x, vex::vector<T> &y, T alpha = 1, bool append = false) const {
+            precondition(x.size() == y.size() && y.nparts() == this->queue.size(), "stencil operator: vectors differ in size or queues");
+            std::vector<const T*> left(this->queue.size(), nullptr), right(this->queue.size(), nullptr);
+            this->exchange_halos(x, left, right);
+            for (unsigned d = 0; d < this->queue.size(); ++d)
+                VEXB_CHECKED(vexb_stencil_operator_apply(this->queue[d].ordinal(), this->queue[d].raw(), id, x(d).raw(), x.part_size(d),
+                                                         left[d], right[d], y(d).raw(), static_cast<double>(alpha), append));
+        }
+    private:
+        int id;
+};
+
 } // namespace vex
+
+/// Declare a user-defined stencil operator type (stencil.hpp:652-657).
+#define VEX_STENCIL_OPERATOR_TYPE(name, type, width, center, body_str) \
+    struct name : vex::StencilOperator<type, width, center, name> { \
+        name(const std::vector<vex::backend::command_queue> &q) : vex::StencilOperator<type, width, center, name>(q) {} \
+        static std::string body() { return body_str; } \
+    }
+/// Declare a user-defined stencil operator (stencil.hpp:667-671).
+#define VEX_STENCIL_OPERATOR(name, type, width, center, body, queue) \
+    VEX_STENCIL_OPERATOR_TYPE(stencil_operator_##name##_t, type, width, center, body) const name(queue)
+
 #endif

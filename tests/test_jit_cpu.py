@@ -110,6 +110,36 @@ def test_ccsr_specialised_kernel_source_compiles(env):
         _ccsr_source(L, np.arange(41), np.zeros(40, np.int32), np.ones(40), compile=False)
 
 
+def test_user_defined_stencil_operator_source_compiles(env):
+    """VEX_STENCIL_OPERATOR (stencil.hpp:510-680): the generated kernel compiles for sm_100a without a device."""
+    vx, api, L, _ = env
+    lib = L.lib()
+
+    def source(dtype, width, center, body, compile=True):
+        k = C.c_int(-1)
+        L.check(lib.vexb_stencil_operator_register(dtype, width, center, body.encode(), C.byref(k)))
+        n = C.c_size_t(0)
+        L.check(lib.vexb_stencil_operator_source(k.value, None, C.byref(n), 0))
+        buf = C.create_string_buffer(n.value + 256)
+        cap = C.c_size_t(len(buf))
+        L.check(lib.vexb_stencil_operator_source(k.value, buf, C.byref(cap), int(compile)))
+        return k.value, buf.value.decode()
+
+    body = "return sin(X[1] - X[0]) + sin(X[0] - X[-1]);"                       # tests/stencil.cpp:187-189
+    k1, src = source(L.F64, 3, 1, body)
+    assert "NVRTC: ok" in src and "typedef double T;" in src and "#define WIDTH 3" in src and "#define CENTER 1" in src
+    assert body in src and "stencil_oper(win + CENTER + threadIdx.x)" in src
+    assert source(L.F64, 3, 1, body, compile=False)[0] == k1                      # same definition, same id
+    k2, src = source(L.F32, 5, 0, "return X[0] + powf(X[1] + X[4], 3.0f);")
+    assert k2 != k1 and "NVRTC: ok" in src and "typedef float T;" in src
+    with pytest.raises(vx.VexbError, match="NVRTC could not compile"):
+        source(L.F64, 3, 1, "return X[0] +;")
+    k = C.c_int(-1)
+    assert lib.vexb_stencil_operator_register(L.F64, 3, 3, b"return X[0];", C.byref(k)) == 2      # center outside the stencil
+    assert lib.vexb_stencil_operator_register(L.I32, 3, 1, b"return X[0];", C.byref(k)) == 2      # integer operators
+    assert lib.vexb_stencil_operator_source(12345, None, C.byref(C.c_size_t(0)), 0) == 2
+
+
 def test_unregistered_call_is_rejected(env):
     vx, api, L, fake_vec = env
     e = L.Expr()

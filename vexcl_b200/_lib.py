@@ -154,6 +154,9 @@ def lib():
         "vexb_ccsr_jit_source": ([sz, vp, vp, vp, i, i, C.c_char_p, P(sz), i], i),
         "vexb_stencil_apply": ([i, vp, i, vp, i, i, vp, sz, vp, vp, vp, d, i], i),
         "vexb_copy_peer": ([i, vp, i, vp, sz, vp], i),
+        "vexb_stencil_operator_register": ([i, i, i, C.c_char_p, P(i)], i),
+        "vexb_stencil_operator_source": ([i, C.c_char_p, P(sz), i], i),
+        "vexb_stencil_operator_apply": ([i, vp, i, vp, sz, vp, vp, vp, d, i], i),
         "vexb_dspmat_create": ([i, vp, i, vp, sz, vp, i, vp, i, vp, i, i, P(vp)], i),
         "vexb_dspmat_destroy": ([vp], i),
         "vexb_dspmat_get_info": ([vp, P(DspmatInfo)], i),

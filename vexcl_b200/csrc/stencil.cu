@@ -15,8 +15,12 @@
 //   * the window is stored with one pad word per 8 elements, so the stride-8 accesses of neighbouring lanes fall in
 //     different banks (stride 9);
 //   * a thread's 8 results leave as 256-bit stores (and `+=` reads y with 256-bit loads).
+#include <mutex>
+#include <string>
+#include <vector>
 #include "common.cuh"
 #include "shapes.cuh"
+#include "jit.hpp"
 
 namespace vexb {
 namespace {
@@ -152,4 +156,101 @@ extern "C" int vexb_copy_peer(int dst_dev, void *dst, int src_dev, const void *s
     if (dst_dev == src_dev) VEXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     else VEXB_CUDA(cudaMemcpyPeerAsync(dst, dst_dev, src, src_dev, bytes, (cudaStream_t)stream));
     return VEXB_OK;
+}
+
+// ---- user-defined stencil operators (VEX_STENCIL_OPERATOR, vexcl/stencil.hpp:510-680) -----------------------------------
+// y[i] (=|+=) alpha * f(X), where the body of f is C source supplied at run time and X[k] is the element k places from
+// i (clamped at the ends of the vector, halos as above).  Like the reference, the kernel is generated per operator:
+// a block stages its window in shared memory and hands the body a pointer into it, so `X[-1]`, `X[0]`, `X[1]` are
+// plain shared-memory reads.  Compiled by NVRTC at first use (--fmad=false), cached per (operator, device).
+namespace vexb {
+namespace {
+struct StencilOp { int dtype, width, center; std::string body; };
+std::mutex g_somx;
+std::vector<StencilOp> g_sops;
+
+std::string stencil_op_source(const StencilOp &op) {
+    const char *T = op.dtype == VEXB_F64 ? "double" : "float";
+    std::string s;
+    s += "// generated by libvexb200 (csrc/stencil.cu): user-defined stencil operator\n";
+    s += std::string("typedef ") + T + " T;\n";
+    s += "#define WIDTH " + std::to_string(op.width) + "\n#define CENTER " + std::to_string(op.center) + "\n";
+    s += "#define RHALO (WIDTH - 1 - CENTER)\n";
+    s += "__device__ __forceinline__ T stencil_oper(const T *X) {\n" + op.body + "\n}\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(256) vexb_stencil_op(const T *__restrict__ x, long long n,\n"
+         "        const T *__restrict__ left, const T *__restrict__ right, T *y, T alpha, int append) {\n"
+         "    __shared__ T win[256 + WIDTH - 1];\n"
+         "    const long long b0 = (long long)blockIdx.x * 256;\n"
+         "    for (int p = threadIdx.x; p < 256 + WIDTH - 1; p += 256) {\n"
+         "        const long long j = b0 - CENTER + p;\n"
+         "        T v;\n"
+         "        if (j < 0) v = left ? left[CENTER + j] : x[0];\n"
+         "        else if (j >= n) { const long long r = j - n; v = (right && RHALO > 0) ? right[r < RHALO ? r : RHALO - 1] : x[n - 1]; }\n"
+         "        else v = x[j];\n"
+         "        win[p] = v;\n"
+         "    }\n"
+         "    __syncthreads();\n"
+         "    const long long i = b0 + threadIdx.x;\n"
+         "    if (i >= n) return;\n"
+         "    const T v = alpha * stencil_oper(win + CENTER + threadIdx.x);\n"
+         "    y[i] = append ? y[i] + v : v;\n"
+         "}\n";
+    return s;
+}
+} // namespace
+} // namespace vexb
+
+extern "C" int vexb_stencil_operator_register(int dtype, int width, int center, const char *body, int *id) {
+    VEXB_CHECK(id && body, "null argument");
+    VEXB_CHECK(dtype == VEXB_F64 || dtype == VEXB_F32, "stencil operators work on float or double");
+    VEXB_CHECK(width >= 1 && width <= 4096 && center >= 0 && center < width, "stencil operator needs 1 <= width <= 4096 and 0 <= center < width");
+    std::lock_guard<std::mutex> lock(vexb::g_somx);
+    for (size_t k = 0; k < vexb::g_sops.size(); ++k) {
+        const auto &o = vexb::g_sops[k];
+        if (o.dtype == dtype && o.width == width && o.center == center && o.body == body) { *id = (int)k; return VEXB_OK; }
+    }
+    vexb::g_sops.push_back({dtype, width, center, body});
+    *id = (int)vexb::g_sops.size() - 1;
+    return VEXB_OK;
+}
+
+extern "C" int vexb_stencil_operator_source(int id, char *buf, size_t *len, int compile) {
+    VEXB_CHECK(len, "len is NULL");
+    std::string src;
+    {
+        std::lock_guard<std::mutex> lock(vexb::g_somx);
+        VEXB_CHECK(id >= 0 && (size_t)id < vexb::g_sops.size(), "unknown stencil operator %d", id);
+        src = vexb::stencil_op_source(vexb::g_sops[(size_t)id]);
+    }
+    if (compile) {
+        size_t bytes = 0; std::string log;
+        VEXB_TRY(vexb::jit_compile_only(src, &bytes, &log));
+        src += "// NVRTC: ok, cubin " + std::to_string(bytes) + " bytes\n";
+    }
+    if (buf) {
+        VEXB_CHECK(*len > src.size(), "buffer too small (%zu <= %zu)", *len, src.size());
+        memcpy(buf, src.c_str(), src.size() + 1);
+    }
+    *len = src.size() + 1;
+    return VEXB_OK;
+}
+
+extern "C" int vexb_stencil_operator_apply(int dev, void *stream, int id, const void *x, size_t n, const void *left,
+                                           const void *right, void *y, double alpha, int append) {
+    vexb::StencilOp op;
+    {
+        std::lock_guard<std::mutex> lock(vexb::g_somx);
+        VEXB_CHECK(id >= 0 && (size_t)id < vexb::g_sops.size(), "unknown stencil operator %d", id);
+        op = vexb::g_sops[(size_t)id];
+    }
+    if (!n) return VEXB_OK;
+    VEXB_CHECK(x && y, "null pointer");
+    VEXB_CHECK(n < ((size_t)1 << 38), "slice too long");
+    DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
+    void *fn = nullptr;
+    VEXB_TRY(vexb::jit_build(dev, vexb::stencil_op_source(op), "vexb_stencil_op", &fn));
+    long long nn = (long long)n;
+    double a64 = alpha; float a32 = (float)alpha;
+    void *args[] = {&x, &nn, &left, &right, &y, op.dtype == VEXB_F64 ? (void *)&a64 : (void *)&a32, &append};
+    return vexb::jit_launch(fn, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, args);
 }
