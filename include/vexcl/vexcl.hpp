@@ -12,6 +12,7 @@
 #include "multivector.hpp"
 #include "function.hpp"
 #include "element_index.hpp"
+#include "constants.hpp"
 #include "tagged_terminal.hpp"
 #include "reductor.hpp"
 #include "spmat.hpp"

@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 export VEXB_RUN_UNVERIFIED=1
 # 1. NVRTC-specialised CCSR kernel + the skipped two-slice C++ stencil run
-timeout 300 python -m pytest tests/test_gpu_unverified.py tests/test_gpu_ccsr.py tests/test_gpu_cpp_frontend.py -q -k "unverified or ccsr or stencil or scalar or 16_bit or pattern" 2>&1 | tail -25 > gpurun_out/r02_unverified_tests.log
+timeout 300 python -m pytest tests/test_gpu_unverified.py tests/test_gpu_ccsr.py tests/test_gpu_cpp_frontend.py -q -k "unverified or ccsr or stencil or scalar or 16_bit or pattern or constants" 2>&1 | tail -25 > gpurun_out/r02_unverified_tests.log
 # 1b. the C++ stencil binary incl. the NVRTC user-defined operator case (one slice, then two)
 for p in 1 2; do VEXCL_TEST_PARTS=$p timeout 120 tests/cpp/bin/test_stencil 12345 2>&1 | tail -4 >> gpurun_out/r02_unverified_tests.log; done
 # 2. the two-slice stencil binary under compute-sanitizer (it stopped after 'two_stencils' in round 1)

@@ -26,16 +26,27 @@ def test_cpp_front_end(built, name, parts):
     assert " 0 failures" in r.stdout
 
 
+@pytest.mark.skipif(not os.environ.get("VEXB_RUN_UNVERIFIED"),
+                    reason="vex::constants was added after the round-1 GPU budget was spent; runs on request until seen green")
+@pytest.mark.parametrize("parts", ["2", "1"])
+def test_cpp_constants(built, parts):
+    _run_binary("test_constants", parts, 120)
+
+
 def _run_stencil(parts: str, timeout: int):
+    _run_binary("test_stencil", parts, timeout)
+
+
+def _run_binary(name: str, parts: str, timeout: int):
     from vexcl_b200 import build
     build.build_cpp_tests()
-    exe = BIN / "test_stencil"
+    exe = BIN / name
     assert exe.exists(), f"{exe} was not built"
     r = subprocess.run([str(exe), "12345"], capture_output=True, text=True, env=dict(os.environ, VEXCL_TEST_PARTS=parts),
                        timeout=timeout)
     print(r.stdout[-3000:])
     print(r.stderr[-3000:])
-    assert r.returncode == 0 and " 0 failures" in r.stdout, f"test_stencil failed:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
+    assert r.returncode == 0 and " 0 failures" in r.stdout, f"{name} failed:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
 
 
 def test_cpp_stencil_single_slice(built):
