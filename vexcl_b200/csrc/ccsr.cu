@@ -198,7 +198,7 @@ static std::string ccsr_jit_source(int val_dtype, int idx_bytes, const std::vect
     const char *I = idx_bytes == 1 ? "unsigned char" : idx_bytes == 2 ? "unsigned short" : "int";
     const char *mul = f64 ? "__dmul_rn" : "__fmul_rn", *add = f64 ? "__dadd_rn" : "__fadd_rn";
     std::string s;
-    char buf[256];
+    char buf[512];
     s += "// generated by libvexb200 (csrc/ccsr.cu) for one CCSR matrix: " + std::to_string(row.size() - 1) + " unique rows, " +
          std::to_string(col.size()) + " entries\n";
     snprintf(buf, sizeof(buf), "extern \"C\" __global__ void __launch_bounds__(256) vexb_ccsr_jit(unsigned long long n, const %s *__restrict__ idx,\n"
