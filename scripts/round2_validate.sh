@@ -10,6 +10,12 @@ timeout 300 python -m pytest tests/test_gpu_unverified.py tests/test_gpu_ccsr.py
 for p in 1 2; do VEXCL_TEST_PARTS=$p timeout 120 tests/cpp/bin/test_stencil 12345 2>&1 | tail -4 >> gpurun_out/r02_unverified_tests.log; done
 # 2. the two-slice stencil binary under compute-sanitizer (it stopped after 'two_stencils' in round 1)
 VEXCL_TEST_PARTS=2 timeout 200 compute-sanitizer --tool memcheck tests/cpp/bin/test_stencil 12345 > gpurun_out/r02_stencil_2slices_memcheck.log 2>&1
+# 2b. host-side memory errors of the header front end: the multivector / stencil tests under ASan + UBSan
+for t in test_multivector test_stencil; do
+  g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -I include tests/cpp/$t.cpp -o /tmp/${t}_asan \
+      -L vexcl_b200 -lvexb200 -Wl,-rpath,$PWD/vexcl_b200 -lpthread -ldl 2>&1 | tail -3
+  ASAN_OPTIONS=protect_shadow_gap=0:detect_leaks=0 VEXCL_TEST_PARTS=2 timeout 200 /tmp/${t}_asan 12345 2>&1 | tail -6 >> gpurun_out/r02_asan.log
+done
 # 3. timings: CCSR variants incl. ccsr.jit, stencil throughput (also in bench.py extra.stencil)
 timeout 100 python - > gpurun_out/r02_ccsr_jit_probe.json 2>&1 <<'PY'
 import json, sys
