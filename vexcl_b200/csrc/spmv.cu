@@ -551,6 +551,7 @@ static bool find_row_patterns(size_t n, const std::vector<int> &rowptr, const st
 template <class T>
 static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col, std::vector<T> &val, int fmt, bool plain) {
     const size_t n = A->nrows_stored;
+    if (fmt == VEXB_FMT_AUTO && param("spmv.auto_patterns", 0)) fmt = VEXB_FMT_PATTERNS;   // off until measured
     if (fmt == VEXB_FMT_PATTERNS) {
         // only for strips whose stored row r is row r of y (no row map) and that are worth it; otherwise as AUTO
         std::vector<int> idx, prow, pcol; std::vector<T> pval;
