@@ -59,7 +59,8 @@ typedef enum {
     VEXB_ERR_INVALID = 2,     /* bad argument / precondition violated     */
     VEXB_ERR_NCCL = 3,        /* NCCL missing or an NCCL call failed      */
     VEXB_ERR_UNSUPPORTED = 4, /* valid request the back end cannot serve  */
-    VEXB_ERR_NOMEM = 5
+    VEXB_ERR_NOMEM = 5,
+    VEXB_ERR_PEER = 6         /* a peer GPU did not arrive in a fused combine / peer-memory halo */
 } vexb_status;
 
 /* Scalar element types (subset of vexcl/types.hpp:202-260). */
@@ -291,8 +292,9 @@ int vexb_graph_destroy(vexb_graph *graph);
  *                         the launcher all-gathers the handles (rank order),
  *                         vexb_peer_connect maps the other ranks' mailboxes;
  *   one process, n GPUs : vexb_peer_create_all (peer access, distinct devices).
- * A rank that never shows up makes the waiting kernel give up after a few
- * seconds and set an error word (vexb_peer_error != 0) instead of hanging.
+ * A rank that never shows up makes the waiting kernel give up after ~20 s:
+ * it stores NaN / all-ones instead of a partial fold and raises a sticky fault
+ * (vexb_peer_error, vexb_peer_fault) instead of hanging.
  * ---------------------------------------------------------------------- */
 typedef struct vexb_peer vexb_peer;
 #define VEXB_IPC_HANDLE_BYTES 64
@@ -301,6 +303,11 @@ int vexb_peer_connect(vexb_peer *peer, const void *handles /* nranks * 64 bytes,
 int vexb_peer_create_all(int ndev, const int *devs, vexb_peer **peers /* ndev out */);
 int vexb_peer_destroy(vexb_peer *peer);
 int vexb_peer_error(vexb_peer *peer, unsigned long long *epoch_of_timeout /* 0 = none */);
+/* Process-wide sticky fault: non-zero once any kernel of this process (fused reduction combine, peer-memory halo)
+ * gave up waiting for a peer.  Such a kernel never folds or multiplies stale data: the values that needed the peer
+ * are written as NaN (floating types) or all-ones (integers).  vexb_reduce_fetch returns VEXB_ERR_PEER while the
+ * fault is set; the front ends turn that into an exception.  clear != 0 resets it (after the group was rebuilt). */
+int vexb_peer_fault(unsigned long long *epoch, int clear);
 /* In-place all-reduce of one value (two for VEXB_MINMAX) per rank. */
 int vexb_peer_allreduce(vexb_peer *peer, void *stream, void *d_buf, int dtype, int op);
 /* vexb_reduce + the combine across the peer group in the same kernel; every rank ends with the
@@ -457,10 +464,43 @@ int vexb_dspmat_mul_remote(const vexb_dspmat *A, void *stream, void *y, double a
 /* Halo exchange for the local parts (grouped ncclSend/ncclRecv): send buffers -> peers' ghost buffers.
  * Replaces spmat.hpp:149-176. */
 int vexb_halo_exchange(int nlocal, vexb_comm *const *comms, vexb_dspmat *const *parts, void *const *streams);
+/* Peer-memory halo (csrc/distapply.cu): when every part is connected, vexb_dspmat_apply is ONE kernel per GPU -- it
+ * stores the x values its neighbours need straight into their ghost buffers over NVLink, multiplies the interior rows,
+ * waits (in the kernel) for its own ghosts and finishes the boundary rows; no NCCL call, no copy, no extra launch, CUDA-
+ * graph replayable.  Replaces spmat.hpp:127-183 in one launch.  Up to 16 parts on distinct devices.
+ *   one process per GPU : vexb_dspmat_halo_handle (64-byte CUDA IPC handle of this part's ghost box), all-gather the
+ *                         handles in part order, vexb_dspmat_halo_connect;
+ *   one process, n GPUs : vexb_dspmat_halo_connect_local (peer access).
+ * Every part of the matrix must then call apply the same number of times (as with NCCL).  A neighbour that never
+ * arrives makes the kernel give up after ~20 s, store NaN in the rows it could not finish and raise vexb_peer_fault. */
+int vexb_dspmat_halo_handle(vexb_dspmat *A, void *handle64);
+int vexb_dspmat_halo_connect(vexb_dspmat *A, const void *handles /* nparts * 64 bytes, part order */);
+int vexb_dspmat_halo_connect_local(int nlocal, vexb_dspmat *const *parts);
+int vexb_dspmat_halo_connected(const vexb_dspmat *A, int *connected);
+int vexb_dspmat_halo_disconnect(vexb_dspmat *A);   /* back to NCCL / copies (e.g. when another rank failed to connect) */
 /* Whole apply for the local parts: pack -> (side stream: exchange) || mul_local -> mul_remote.
  * x[k], y[k] are the device slices of part k.  comms may be NULL when there are no ghosts. */
 int vexb_dspmat_apply(int nlocal, vexb_comm *const *comms, vexb_dspmat *const *parts, void *const *streams,
                       const void *const *x, void *const *y, double alpha, int append);
+
+/* The product and a dot product with its result in ONE launch per GPU: y (=|+=) alpha*A*x, then
+ * d_result[k][0] = sum over all parts of dot_with . y (same bits on every GPU; combined through the peer group inside
+ * the kernel).  With dot_with = x this is q = A*p, (p, q) of a CG iteration.  Needs the peer-memory halo on every part
+ * (or a single part) and a hybrid-ELL interior strip; returns VEXB_ERR_UNSUPPORTED otherwise (compose apply + reduce). */
+int vexb_dspmat_apply_dot(int nlocal, vexb_dspmat *const *parts, void *const *streams, const void *const *x,
+                          void *const *y, double alpha, int append, const void *const *dot_with,
+                          void *const *d_result, vexb_peer *const *peers);
+
+/* The vector half of a conjugate-gradient iteration (BASELINE configs[4]) in two sweeps, scalars device-resident:
+ *   vexb_cg_update_r  : alpha = *d_rho / *d_pq;  r -= alpha q;  *d_rho_new = (r, r)   (folded like vexb_reduce, combined
+ *                       over `peer` in the same kernel; peer == NULL: this slice only)             24 bytes per row
+ *   vexb_cg_update_xp : alpha as above, beta = *d_rho_new / *d_rho;  x += alpha p;  p = r + beta p  40 bytes per row
+ * Same unfused per-element arithmetic as the vexb_eval / vexb_reduce composition (viennacl.hpp:36-64 composes CG from
+ * those); d_workspace as for vexb_reduce.  Vectors must be 32-byte aligned (vexb_malloc's are). */
+int vexb_cg_update_r(int dev, void *stream, int dtype, size_t n, void *r, const void *q,
+                     const void *d_rho, const void *d_pq, void *d_rho_new, void *d_workspace, vexb_peer *peer);
+int vexb_cg_update_xp(int dev, void *stream, int dtype, size_t n, void *x, void *p, const void *r,
+                      const void *d_rho, const void *d_pq, const void *d_rho_new);
 
 #ifdef __cplusplus
 }

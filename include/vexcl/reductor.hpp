@@ -144,6 +144,16 @@ class Reductor {
                     detail::assign_expression<assign::SET>(tmp, expr, comp);
                     return reduce(tmp, -1);
                 }
+                if (st != VEXB_OK && fused && d > 0) {
+                    // devices 0..d-1 have already launched and will wait for everybody in the kernel: keep the group in step
+                    // (identity + the standalone combine on the devices that did not launch), then report the failure
+                    const std::string why = vexb_last_error();
+                    for (unsigned e = d; e < queue.size(); ++e) {
+                        vexb_reduce_identity(queue[e].ordinal(), queue[e].raw(), dt, op, res[e].raw());
+                        vexb_peer_allreduce(ps->peers[e], queue[e].raw(), res[e].raw(), dt, op);
+                    }
+                    throw backend::error(st, why);
+                }
                 VEXB_CHECKED(st);
             }
             auto cs = (queue.size() > 1 && !fused) ? detail::communicators(queue) : std::shared_ptr<detail::comm_set>();

@@ -8,8 +8,10 @@
  *   - strips are stored with 32-bit local indices and multiplied by hand-written sm_100a
  *     kernels (row-block CSR stream with TMA staging, or hybrid ELL; libvexb200 picks);
  *   - the ghost exchange (reference: D2H, host shuffle, H2D with three host syncs,
- *     spmat.hpp:137-175) is grouped ncclSend/ncclRecv between device buffers on a side stream,
- *     overlapped with the local product; nothing in apply() waits on the host.
+ *     spmat.hpp:137-175) happens inside the product kernel: it stores the values its neighbours
+ *     need straight into their ghost buffers over NVLink peer memory and waits for its own
+ *     (one launch per device and product; csrc/distapply.cu).  Without peer access: grouped
+ *     ncclSend/ncclRecv on a side stream.  Nothing in apply() waits on the host.
  */
 #include <memory>
 #include "reductor.hpp"
@@ -56,7 +58,15 @@ class SpMat {
                                                 col + row[part[d]], sizeof(col_t), val + row[part[d]], dtype_of<val_t>::value,
                                                 format, &mtx[d]));
             }
-            if (nd > 1 && off[nd] > 0) comms = detail::communicators(queue);
+            if (nd > 1 && off[nd] > 0) {
+                // distinct devices with peer access: the halo is pushed through NVLink peer memory inside the product kernel
+                // (one launch per device and product); otherwise NCCL send/recv or copy-engine copies
+                bool distinct = nd <= 16;
+                for (int a = 0; distinct && a < nd; ++a) for (int b = a + 1; b < nd; ++b) if (queue[a].ordinal() == queue[b].ordinal()) distinct = false;
+                peer_halo = distinct && vexb_dspmat_halo_connect_local(nd, mtx.data()) == VEXB_OK;
+                if (distinct && !peer_halo) for (auto m : mtx) vexb_dspmat_halo_disconnect(m);
+                if (!peer_halo) comms = detail::communicators(queue);
+            }
         }
 
         SpMat(const SpMat&) = delete;
@@ -89,11 +99,12 @@ class SpMat {
         vexb_halo_plan *plan;
         std::vector<vexb_dspmat*> mtx;
         std::shared_ptr<detail::comm_set> comms;
+        bool peer_halo = false;
 
         void swap(SpMat &o) {
             std::swap(queue, o.queue); std::swap(part, o.part); std::swap(col_part, o.col_part);
             std::swap(nrows, o.nrows); std::swap(ncols, o.ncols); std::swap(nnz, o.nnz);
-            std::swap(plan, o.plan); std::swap(mtx, o.mtx); std::swap(comms, o.comms);
+            std::swap(plan, o.plan); std::swap(mtx, o.mtx); std::swap(comms, o.comms); std::swap(peer_halo, o.peer_halo);
         }
 };
 

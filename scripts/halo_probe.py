@@ -48,9 +48,9 @@ res["pack_us"] = timeit(lambda: L.check(lib.vexb_dspmat_pack(h, ctx.streams[k], 
 res["remote_us"] = timeit(lambda: L.check(lib.vexb_dspmat_mul_remote(h, ctx.streams[k], y.bufs[k], 1.0)))
 comms = ctx._arr(ctx.comms); parts = ctx._arr(A.parts); streams = ctx._arr(ctx.streams)
 res["exchange_only_us"] = timeit(lambda: L.check(lib.vexb_halo_exchange(1, comms, parts, streams)))
-vx.set_param("dspmat.debug_skip_exchange", 1)
-res["apply_no_exchange_us"] = timeit(lambda: A.apply(x, y, 1.0, False))
-vx.set_param("dspmat.debug_skip_exchange", 0)
+vx.set_param("dspmat.no_peer_halo", 1)            # the NCCL send/recv path (pack, exchange, interior, two boundary kernels)
+res["apply_nccl_path_us"] = timeit(lambda: A.apply(x, y, 1.0, False))
+vx.set_param("dspmat.no_peer_halo", 0)
 res["n_ghost"] = int(info.n_ghost); res["n_send"] = int(info.n_send); res["loc_fmt"] = int(info.loc.fmt); res["loc_rows"] = int(info.loc.nrows)
 if rank == 0: print(json.dumps(res))
 barrier(); dist.destroy_process_group()

@@ -100,11 +100,9 @@ BOOST_AUTO_TEST_CASE(single_precision)
     for (size_t i = 0; i < n; ++i) BOOST_CHECK(back[i] == convolve_at(taps, 10, host.data(), n, i, 0.0f));
 }
 
-// tests/stencil.cpp:183-217 (user_defined_stencil).  The operator is compiled by NVRTC when first applied; until that
-// path has been seen on a GPU the case only runs on request (VEXB_RUN_UNVERIFIED=1).
+// tests/stencil.cpp:183-217 (user_defined_stencil).  The operator is compiled by NVRTC when first applied.
 BOOST_AUTO_TEST_CASE(user_defined_stencil)
 {
-    if (!std::getenv("VEXB_RUN_UNVERIFIED")) return;
     const size_t n = 1024;
     VEX_STENCIL_OPERATOR(oscillate, double, 3, 1, "return sin(X[1] - X[0]) + sin(X[0] - X[-1]);", ctx);
     const std::vector<double> host = random_vector<double>(n);

@@ -11,11 +11,8 @@ from vexcl_b200 import gen
 pytestmark = pytest.mark.gpu
 
 
-import os
-
-# "jit" = the matrix-specialised NVRTC kernel (ccsr.jit): written after the round-1 GPU budget was spent, so it only
-# runs on request until it has been seen green on a GPU.
-VARIANTS = [1, 2, 3] + (["jit"] if os.environ.get("VEXB_RUN_UNVERIFIED") else [])
+# "jit" = the matrix-specialised NVRTC kernel (ccsr.jit): the unique rows become code.
+VARIANTS = [1, 2, 3, "jit"]
 
 
 @pytest.fixture(params=VARIANTS, autouse=True)

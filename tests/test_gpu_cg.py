@@ -80,3 +80,56 @@ def test_cg_device_scalars_and_graph(ctx1):
         ctx1.finish()
         assert abs(cg.residual2() - hist_o[-1]) <= 1e-8 * hist_o[-1]
         assert np.allclose(x.read(), xo, rtol=1e-8, atol=1e-12)
+
+
+def test_product_with_fused_dot(ctx1):
+    ctx = ctx1
+    """SpMat.apply_dot: y = alpha*A*x (+ y) and dot(w, y) in one launch when the strip is hybrid ELL on a single part
+    (vexb_dspmat_apply_dot); the composition otherwise (several slots on one device, CSR).  Same y bits as apply."""
+    row, col, val, b, N = problem(16)
+    X, W, Y0 = oracle.uniform_real(4, N), oracle.uniform_real(5, N), oracle.uniform_real(6, N)
+    for fmt in (L.FMT_HELL, L.FMT_CSR):
+        A = vx.SpMat(ctx, N, N, row, col, val, fmt)
+        x, w, y, y2 = vx.vector(ctx, X), vx.vector(ctx, W), vx.vector(ctx, Y0), vx.vector(ctx, Y0)
+        d = DeviceScalar(ctx)
+        for dot_with, alpha, append in ((None, 1.0, False), (w, -0.5, True)):
+            fused = A.apply_dot(x, y, d, dot_with=dot_with, alpha=alpha, append=append)
+            assert fused == (fmt == L.FMT_HELL and ctx.nparts == 1)
+            A.apply(x, y2, alpha, append)
+            got = y.read()
+            assert np.array_equal(got, y2.read())
+            ref = float(np.dot(X if dot_with is None else W, got))
+            assert abs(d.get() - ref) <= 1e-10 * np.sum(np.abs((X if dot_with is None else W) * got))
+
+
+def test_fused_cg_matches_oracle(ctx1):
+    ctx = ctx1
+    """CGFused: product + dot, r sweep + (r, r), x/p sweep -- three launches per iteration on one GPU; same history as the
+    oracle's composition, stream-launched and replayed as two alternating CUDA graphs."""
+    from vexcl_b200.solvers import CGFused
+    row, col, val, b, N = problem()
+    iters = 25
+    xo, hist_o = oracle.cg(row, col, val, b, np.zeros(N), iters)
+    A = vx.SpMat(ctx, N, N, row, col, val)
+    for use_graph in (False, True):
+        bv, x = vx.vector(ctx, b), vx.vector(ctx, N)
+        x.assign(0.0)
+        cg = CGFused(A, bv, x)
+        hist = []
+        if use_graph:
+            cg.capture()                                   # performs iterations 1 and 2 while warming up
+            done = 2
+        else:
+            done = 0
+        for _ in range(iters - done):
+            cg.run(1)
+            hist.append(cg.residual2())
+        ctx.finish()
+        assert np.allclose(hist, hist_o[done:], rtol=1e-8)
+        assert np.allclose(x.read(), xo, rtol=1e-8, atol=1e-12)
+        if ctx.nparts == 1:
+            assert cg.fused_product
+        n0 = vx.launch_count()
+        cg.step()
+        if ctx.nparts == 1:
+            assert vx.launch_count() - n0 == 3             # the iteration IS three kernels

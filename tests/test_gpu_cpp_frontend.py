@@ -26,8 +26,6 @@ def test_cpp_front_end(built, name, parts):
     assert " 0 failures" in r.stdout
 
 
-@pytest.mark.skipif(not os.environ.get("VEXB_RUN_UNVERIFIED"),
-                    reason="vex::constants was added after the round-1 GPU budget was spent; runs on request until seen green")
 @pytest.mark.parametrize("parts", ["2", "1"])
 def test_cpp_constants(built, parts):
     _run_binary("test_constants", parts, 120)
@@ -54,12 +52,6 @@ def test_cpp_stencil_single_slice(built):
     _run_stencil("1", 300)
 
 
-@pytest.mark.skipif(not os.environ.get("VEXB_RUN_UNVERIFIED"),
-                    reason="round 1: with two slices on one device the binary stopped after 'two_stencils' in the one GPU "
-                           "run there was budget for (no output, killed by a 20 s limit); the same front-end logic passes "
-                           "against a host stand-in of the ABI and the Python mirror passes the 2- and 3-slice cases on "
-                           "the GPU (tests/test_gpu_stencil.py).  Set VEXB_RUN_UNVERIFIED=1 to run it (round 2: under "
-                           "compute-sanitizer).")
 def test_cpp_stencil_two_slices(built):
     try:
         _run_stencil("2", 90)

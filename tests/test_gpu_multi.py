@@ -24,12 +24,16 @@ def ndev():
     return n.value
 
 
-@pytest.fixture(scope="module")
-def ctxn(built):
+@pytest.fixture(scope="module", params=["nccl", "peer"])
+def ctxn(request, built):
+    """Several GPUs driven by one process: halo over NCCL send/recv, or pushed through peer memory inside the product
+    kernel (the default on distinct devices)."""
     n = ndev()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    return vx.Context(list(range(min(n, 4))), use_nccl=True)
+    if request.param == "nccl":
+        return vx.Context(list(range(min(n, 4))), use_nccl=True, peer_halo=False)
+    return vx.Context(list(range(min(n, 4))), use_peer=True)
 
 
 def test_nccl_reduce_and_halo_single_process(ctxn):
@@ -56,7 +60,12 @@ def test_nccl_reduce_and_halo_single_process(ctxn):
             for _ in range(3):                                   # repeated applies reuse the halo buffers
                 y.assign(A * xv)
             mag = oracle.csr_absrow(row, col, val, Xv)
+            assert A.peer_halo == ctxn.peer_halo
             assert np.all(np.abs(y.read() - want) <= 1e-10 * mag)
+            if A.peer_halo and fmt == vx.FMT_HELL:
+                n0 = vx.launch_count()
+                A.apply(xv, y, 1.0, False)
+                assert vx.launch_count() - n0 == nd           # ONE kernel per device and product
             y += 2 * (A * xv)
             assert np.all(np.abs(y.read() - 3 * want) <= 3e-10 * mag)
     row, col, val = oracle.random_matrix(5000, 5000, 12, seed=77)
@@ -104,10 +113,60 @@ def test_fused_reduce_allreduce_over_peer_memory(built):
     assert err.value == 0
 
 
+def test_peer_halo_many_products_graph_and_fused_cg(built):
+    """Epoch parity, acknowledgements and CUDA-graph replay of the fused product over many iterations; then the fused CG
+    iteration (product + dot combined across the GPUs inside the kernel) against the oracle."""
+    n = ndev()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from vexcl_b200.api import Graph
+    from vexcl_b200.solvers import CGFused
+    ctx = vx.Context(list(range(min(n, 8))), use_peer=True)
+    row, col, val = oracle.poisson(3, 40)
+    N = row.size - 1
+    Xv = oracle.uniform_real(7, N)
+    A = vx.SpMat(ctx, N, N, row, col, val)
+    assert A.peer_halo
+    x, y = vx.vector(ctx, Xv), vx.vector(ctx, N)
+    want = oracle.csr_spmv(row, col, val, Xv)
+    mag = oracle.csr_absrow(row, col, val, Xv)
+    for _ in range(7):
+        A.apply(x, y, 1.0, False)
+    assert np.all(np.abs(y.read() - want) <= 1e-10 * mag)
+    g = Graph(ctx, lambda: A.apply(x, y, 1.0, False))
+    for it in range(40):                                         # x changes between replays: stale ghosts would show
+        x.assign(x * 0.5 + 0.25)
+        Xv = Xv * 0.5 + 0.25
+        g.launch()
+    ctx.finish()
+    assert np.all(np.abs(y.read() - oracle.csr_spmv(row, col, val, Xv)) <= 1e-10 * oracle.csr_absrow(row, col, val, Xv))
+    # fused CG on an SPD problem
+    from vexcl_b200 import gen
+    row, col, val = gen.poisson_strip(3, 24, 20, 8 * ctx.nparts, spd=True)
+    N = row.size - 1
+    b = oracle.uniform_real(3, N)
+    xo, hist_o = oracle.cg(row, col, val, b, np.zeros(N), 20)
+    A = vx.SpMat(ctx, N, N, row, col, val)
+    bv, xs = vx.vector(ctx, b), vx.vector(ctx, N)
+    xs.assign(0.0)
+    cg = CGFused(A, bv, xs)
+    cg.capture()
+    hist = []
+    for _ in range(18):
+        cg.run(1)
+        hist.append(cg.residual2())
+    assert cg.fused_product
+    assert np.allclose(hist, hist_o[2:], rtol=1e-8)
+    assert np.allclose(xs.read(), xo, rtol=1e-8, atol=1e-12)
+    e = C.c_uint64(7)
+    L.check(L.lib().vexb_peer_fault(C.byref(e), 0))
+    assert e.value == 0
+
+
 def test_copy_engine_halo_without_nccl(built):
     if ndev() < 2:
         pytest.skip("needs >= 2 GPUs")
-    ctx = vx.Context([0, 1], use_nccl=False)
+    ctx = vx.Context([0, 1], use_nccl=False, peer_halo=False)
     row, col, val = oracle.poisson(2, 150)
     N = row.size - 1
     Xv = oracle.uniform_real(7, N)

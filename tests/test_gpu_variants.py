@@ -1,37 +1,55 @@
-"""Kernel variants written in round 1 AFTER the GPU budget was spent.  They are opt-in in the library (tunables) and
-these tests only run on request (VEXB_RUN_UNVERIFIED=1, see scripts/round2_validate.sh), so that an unseen failure
-cannot turn the suite red.  Once seen green on a GPU they move into the regular files."""
-import os
-
+"""Selectable kernel variants and storage encodings of the sparse strips: the CSR thread-per-row kernel
+(spmv.kernel=3), hybrid ELL with 16-bit column offsets (spmv.col16) and row-pattern strips (VEXB_FMT_PATTERNS).
+First seen green on a B200 in round 2 (profiles/r02_validate_unverified.log)."""
 import numpy as np
 import pytest
 
 import oracle
 import vexcl_b200 as vx
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("VEXB_RUN_UNVERIFIED"), reason="unverified variants run on request only")]
+pytestmark = pytest.mark.gpu
+
+
+# spmv.kernel: 0 = TMA-staged CTA tiles, 1 = persistent TMA pipeline, 2 = register-staged CTA tiles, 3 = thread per row,
+# 4 = warp tiles, -1 = the strip's own choice (3 for short even rows, else 4)
+@pytest.fixture(params=[3, 4, 0, 1, 2, -1])
+def csr_kernel(request, built):
+    vx.set_param("spmv.kernel", request.param)
+    yield request.param
+    vx.set_param("spmv.kernel", -1)
 
 
 @pytest.fixture
 def scalar_csr(built):
     vx.set_param("spmv.kernel", 3)                       # csr_scalar_kernel: one thread per row
     yield
-    vx.set_param("spmv.kernel", 0)
+    vx.set_param("spmv.kernel", -1)
+
+
+def _irregular(n, seed, lo=0, hi=32, long_rows=()):
+    """Rows of width U[lo, hi) (plus a few given long ones), sorted distinct columns."""
+    rng = np.random.default_rng(seed)
+    w = rng.integers(lo, hi, n)
+    for i, L_ in long_rows:
+        w[i] = L_
+    row = np.concatenate([[0], np.cumsum(w)]).astype(np.int64)
+    col = np.concatenate([np.sort(rng.choice(n, size=k, replace=False)) for k in w]).astype(np.int64) if row[-1] else np.empty(0, np.int64)
+    return row, col, rng.random(int(row[-1])) - 0.5
 
 
 @pytest.mark.parametrize("nparts", [1, 2, 3])
-def test_csr_scalar_kernel_matches_the_oracle(scalar_csr, ctx1, ctx2, ctx3, nparts):
+def test_csr_kernels_match_the_oracle(csr_kernel, ctx1, ctx2, ctx3, nparts):
     ctx = {1: ctx1, 2: ctx2, 3: ctx3}[nparts]
-    for row, col, val in (oracle.poisson(2, 96), oracle.poisson(3, 20), oracle.random_matrix(3000, 3000, 16, seed=4),
-                          oracle.tridiagonal(1024)):
+    cases = [oracle.poisson(2, 96), oracle.poisson(3, 20), oracle.random_matrix(3000, 3000, 16, seed=4), oracle.tridiagonal(1024),
+             _irregular(5000, 1), _irregular(3000, 2, 20, 90), _irregular(2500, 3, 0, 8, long_rows=((7, 300), (1200, 2400), (2499, 257)))]
+    for row, col, val in cases:
         n = row.size - 1
         xh = oracle.uniform_real(9, n)
         A = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_CSR)
         x, y = vx.vector(ctx, xh), vx.vector(ctx, n)
         y.assign(A * x)
         want = oracle.csr_spmv(row, col, val, xh)
-        if nparts == 1:
+        if nparts == 1 and csr_kernel == 3:
             assert np.array_equal(y.read(), want)        # storage-order sums without contraction: exact
         else:
             assert np.all(np.abs(y.read() - want) <= 1e-10 * oracle.csr_absrow(row, col, val, xh))
@@ -50,11 +68,11 @@ def test_csr_scalar_kernel_single_precision(scalar_csr, ctx1):
     assert np.allclose(y.read(), want, rtol=2e-5, atol=1e-5)
 
 
-@pytest.fixture
-def col16(built):
-    vx.set_param("spmv.col16", 1)                        # hybrid ELL with 16-bit column offsets (read at construction)
+@pytest.fixture(params=[1, 0])
+def col16(request, built):
+    vx.set_param("spmv.col16", request.param)            # hybrid ELL with 16-bit column offsets (read at construction; default on)
     yield
-    vx.set_param("spmv.col16", 0)
+    vx.set_param("spmv.col16", 1)
 
 
 @pytest.mark.parametrize("nparts", [1, 2, 3])

@@ -87,7 +87,7 @@ def _ccsr_source(L, row, col, val, idx_bytes=1, compile=True):
 
 def test_ccsr_specialised_kernel_source_compiles(env):
     """The matrix-specialised CCSR kernel (csrc/ccsr.cu, tunable ccsr.jit): unique rows become code.  NVRTC compiles it
-    for sm_100a without a device; running it is a GPU test (tests/test_gpu_ccsr.py, VEXB_RUN_UNVERIFIED in round 1)."""
+    for sm_100a without a device; running it is a GPU test (tests/test_gpu_ccsr.py)."""
     vx, api, L, _ = env
     from vexcl_b200 import gen
     idx, row, col, val = gen.poisson_ccsr(32)

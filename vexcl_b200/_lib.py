@@ -12,6 +12,7 @@ HEADER = _HERE.parent / "include" / "vexb200.h"
 
 # enums (mirrors of include/vexb200.h)
 OK = 0
+ERR_CUDA, ERR_INVALID, ERR_NCCL, ERR_UNSUPPORTED, ERR_NOMEM, ERR_PEER = range(1, 7)
 F64, F32, I32, U32, I64, U64 = range(6)
 SET, ADD, SUB, MUL, DIV, MOD, AND, OR, XOR, LSH, RSH = range(11)
 SUM, SUM_KAHAN, MAX, MIN, MINMAX = range(5)
@@ -168,6 +169,13 @@ def lib():
         "vexb_dspmat_mul_remote": ([vp, vp, vp, d], i),
         "vexb_halo_exchange": ([i, P(vp), P(vp), P(vp)], i),
         "vexb_dspmat_apply": ([i, P(vp), P(vp), P(vp), P(vp), P(vp), d, i], i),
+        "vexb_dspmat_halo_handle": ([vp, vp], i), "vexb_dspmat_halo_connect": ([vp, vp], i),
+        "vexb_dspmat_halo_connect_local": ([i, P(vp)], i), "vexb_dspmat_halo_connected": ([vp, P(i)], i),
+        "vexb_dspmat_halo_disconnect": ([vp], i),
+        "vexb_dspmat_apply_dot": ([i, P(vp), P(vp), P(vp), P(vp), d, i, P(vp), P(vp), P(vp)], i),
+        "vexb_peer_fault": ([P(C.c_uint64), i], i),
+        "vexb_cg_update_r": ([i, vp, i, sz, vp, vp, vp, vp, vp, vp, vp], i),
+        "vexb_cg_update_xp": ([i, vp, i, sz, vp, vp, vp, vp, vp, vp], i),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)          # AttributeError here == the library does not export a declared symbol

@@ -68,7 +68,10 @@ class Context:
     """A list of (device, stream) pairs, one per partition slot."""
     use_peer_reduce = True          # combine reductions through peer memory when a peer group exists
 
-    def __init__(self, devices: Sequence[int] = (0,), use_nccl: Optional[bool] = None, weights=None, use_peer: bool = False):
+    def __init__(self, devices: Sequence[int] = (0,), use_nccl: Optional[bool] = None, weights=None, use_peer: bool = False,
+                 peer_halo: Optional[bool] = None):
+        """peer_halo: push SpMat halos through NVLink peer memory inside the product kernel (None: whenever the slots
+        sit on distinct devices that can access each other; False: NCCL send/recv or copy-engine copies)."""
         lib = L.lib()
         L.check(lib.vexb_init())
         self.nparts = len(devices)
@@ -92,6 +95,7 @@ class Context:
             out = (C.c_void_p * self.nparts)()
             L.check(lib.vexb_comm_create_all(self.nparts, arr, out))
             self.comms = {k: C.c_void_p(out[k]) for k in range(self.nparts)}
+        self.peer_halo = (distinct and self.nparts > 1) if peer_halo is None else bool(peer_halo)
         self.peers = None
         if use_peer and self.nparts > 1:
             if not distinct:
@@ -104,7 +108,7 @@ class Context:
 
     @classmethod
     def distributed(cls, rank: int, nranks: int, dev: int, unique_id: bytes,
-                    allgather: Callable[[np.ndarray], list], use_peer: bool = True):
+                    allgather: Callable[[np.ndarray], list], use_peer: bool = True, peer_halo: Optional[bool] = None):
         """One process per device.  `unique_id`: the 128 bytes produced by rank 0's
         comm_unique_id() and broadcast by the launcher; `allgather(arr)` returns the list of every
         rank's int64 array (used once, at SpMat construction, to share ghost column lists)."""
@@ -125,6 +129,7 @@ class Context:
             L.check(lib.vexb_comm_create_rank(dev, nranks, rank, buf, C.byref(c)))
             self.comms = {rank: c}
         self.allgather = allgather
+        self.peer_halo = (nranks > 1 and use_peer) if peer_halo is None else bool(peer_halo)
         self.peers = None
         if nranks > 1 and use_peer:
             # peer-memory group: exchange the CUDA IPC handles of the mailboxes through the launcher's all-gather
@@ -617,6 +622,29 @@ class vector(Node):
         return buf.value.decode()
 
 
+def _reduce_all_in_step(ctx, k, peer, dtype, kind, result, code, results):
+    """A fused reduction that fails on slot k after earlier slots have launched would leave those kernels waiting for a
+    peer that never comes and the mailbox epochs out of step: run the identity + the standalone combine on the slots that
+    did not launch, then raise."""
+    if code == L.OK:
+        return
+    msg = L.lib().vexb_last_error().decode(errors="replace")
+    if peer is not None and len(ctx.local) > 1:
+        lib = L.lib()
+        for j in ctx.local[ctx.local.index(k):]:
+            lib.vexb_reduce_identity(ctx.devs[j], ctx.streams[j], dtype, kind, results[j])
+            lib.vexb_peer_allreduce(ctx.peers[j], ctx.streams[j], results[j], dtype, kind)
+    raise L.VexbError(code, msg)
+
+
+def check_peer_fault():
+    """Raise if any kernel of this process gave up waiting for a peer GPU (its results are NaN / all-ones, never stale)."""
+    e = C.c_uint64(0)
+    L.lib().vexb_peer_fault(C.byref(e), 0)
+    if e.value:
+        raise L.VexbError(L.ERR_PEER, f"a peer GPU did not arrive within the time limit (epoch {e.value}); dependent results are poisoned")
+
+
 # ------------------------------------------------------------------------------------------- Reductor
 class Reductor:
     """vex::Reductor<T, RDC> (reductor.hpp:289-439).  kind: L.SUM, L.SUM_KAHAN, L.MAX, L.MIN, L.MINMAX."""
@@ -641,8 +669,9 @@ class Reductor:
             low = _Lowering(k, int(part[k]))
             low.lower(expr)
             peer = ctx.peers[k] if (ctx.peers is not None and ctx.use_peer_reduce and ctx.nparts > 1) else None
-            L.check(lib.vexb_reduce_all(ctx.devs[k], ctx.streams[k], C.byref(low.e), self.dtype, int(part[k + 1] - part[k]),
-                                        int(part[k]), self.kind, r, ws, peer))
+            _reduce_all_in_step(ctx, k, peer, self.dtype, self.kind, r,
+                                lib.vexb_reduce_all(ctx.devs[k], ctx.streams[k], C.byref(low.e), self.dtype, int(part[k + 1] - part[k]),
+                                                    int(part[k]), self.kind, r, ws, peer), {j: ctx.workspace(j)[1] for j in ctx.local})
             res[k] = r
         out = np.empty(cnt, dtype=self.np_dtype)
         if ctx.nparts > 1 and ctx.peers is not None and ctx.use_peer_reduce:
@@ -740,6 +769,30 @@ class SpMat:
                                            _ip(pval), self.val_dtype, fmt, C.byref(h)))
             self.parts[k] = h
         self._strips = None
+        self.peer_halo = False
+        if ctx.nparts > 1 and ctx.nparts <= 16 and getattr(ctx, "peer_halo", False):
+            self.peer_halo = self._connect_peer_halo()
+
+    def _connect_peer_halo(self) -> bool:
+        """Map the neighbours' ghost boxes (CUDA IPC between processes, peer access inside one).  All or nothing across
+        the parts: if any part cannot connect, every part goes back to NCCL / copies (no rank may wait on a missing peer)."""
+        lib, ctx = L.lib(), self.ctx
+        if ctx.is_distributed:
+            k = ctx.local[0]
+            h = C.create_string_buffer(64)
+            ok = lib.vexb_dspmat_halo_handle(self.parts[k], h) == L.OK
+            allh = ctx.allgather(np.frombuffer(h.raw, dtype=np.uint8).copy())
+            if ok:
+                cat = b"".join(np.asarray(a, dtype=np.uint8).tobytes() for a in allh)
+                ok = lib.vexb_dspmat_halo_connect(self.parts[k], C.create_string_buffer(cat, 64 * ctx.nparts)) == L.OK
+            everybody = ctx.allgather(np.array([1 if ok else 0], dtype=np.int64))
+            ok = all(int(np.asarray(a)[0]) == 1 for a in everybody)
+        else:
+            ok = lib.vexb_dspmat_halo_connect_local(len(ctx.local), ctx._arr(self.parts)) == L.OK
+        if not ok:
+            for h in self.parts.values():
+                lib.vexb_dspmat_halo_disconnect(h)
+        return ok
 
     def __del__(self):
         try:
@@ -773,6 +826,33 @@ class SpMat:
         L.check(L.lib().vexb_dspmat_apply(len(ctx.local), comms, ctx._arr(self.parts), ctx._arr(ctx.streams),
                                           ctx._arr(x.bufs), ctx._arr(y.bufs), float(alpha), int(append)))
         return y
+
+
+def _spmat_apply_dot(self, x: "vector", y: "vector", out: "DeviceScalar", dot_with: Optional["vector"] = None,
+                     alpha: float = 1.0, append: bool = False) -> bool:
+    """y (=|+=) alpha*A*x and out = dot(dot_with or x, y) on every device.  One launch per GPU when the matrix has the
+    peer-memory halo (or a single part) and a hybrid-ELL interior (vexb_dspmat_apply_dot); otherwise the product followed
+    by a device-resident reduction.  Returns True when the fused kernel ran."""
+    ctx, lib = self.ctx, L.lib()
+    w = x if dot_with is None else dot_with
+    if x.n != self.m or y.n != self.n or w.n != self.n:
+        raise ValueError("SpMat::apply_dot: vector sizes do not match the matrix")
+    if getattr(self, "_fused_dot", True):
+        peers = ctx._arr(ctx.peers) if (ctx.peers is not None and ctx.nparts > 1) else None
+        if ctx.nparts == 1 or peers is not None:
+            code = lib.vexb_dspmat_apply_dot(len(ctx.local), ctx._arr(self.parts), ctx._arr(ctx.streams), ctx._arr(x.bufs),
+                                             ctx._arr(y.bufs), float(alpha), int(append), ctx._arr(w.bufs), ctx._arr(out.bufs), peers)
+            if code == L.OK:
+                return True
+            if code != L.ERR_UNSUPPORTED:
+                L.check(code)
+        self._fused_dot = False                        # not available for this matrix: do not ask again
+    self.apply(x, y, alpha, append)
+    Reductor(ctx, w.np_dtype, L.SUM).device(w * y, out)
+    return False
+
+
+SpMat.apply_dot = _spmat_apply_dot
 
 
 class SpMatCCSR:
@@ -995,6 +1075,7 @@ class DeviceScalar(Node):
         k = self.ctx.local[0]
         h = np.empty(1, dtype=self.np_dtype)
         L.check(L.lib().vexb_d2h(self.ctx.devs[k], h.ctypes.data, self.bufs[k], self.np_dtype.itemsize, self.ctx.streams[k], 1))
+        check_peer_fault()
         return h[0]
 
     def assign(self, rhs):
@@ -1039,8 +1120,9 @@ def _reduce_device(self, expr, out: DeviceScalar):
         low.lower(expr)
         # with a peer group the combine across GPUs happens inside the reduction kernel (no NCCL call)
         peer = ctx.peers[k] if (ctx.peers is not None and ctx.use_peer_reduce) else None
-        L.check(lib.vexb_reduce_all(ctx.devs[k], ctx.streams[k], C.byref(low.e), self.dtype, int(part[k + 1] - part[k]),
-                                    int(part[k]), self.kind, out.bufs[k], ws, peer))
+        _reduce_all_in_step(ctx, k, peer, self.dtype, self.kind, out.bufs[k],
+                            lib.vexb_reduce_all(ctx.devs[k], ctx.streams[k], C.byref(low.e), self.dtype, int(part[k + 1] - part[k]),
+                                                int(part[k]), self.kind, out.bufs[k], ws, peer), out.bufs)
     if ctx.nparts > 1 and not (ctx.peers is not None and ctx.use_peer_reduce):
         if ctx.comms is None:
             raise RuntimeError("device-resident reductions over several slots need a communicator (NCCL)")

@@ -12,27 +12,11 @@
 // The remote strip stores only rows that have remote entries (row-compressed),
 // so mul_remote touches y only where a ghost contributes; rows without ghosts
 // are left alone where the reference adds alpha*0.
-#include "spmat.hpp"
+#include "dspmat.hpp"
 #include "comm.hpp"
+#include "peer.cuh"
+#define VEXB_MAX_HALO_PARTS VEXB_MAX_PEERS
 #include <algorithm>
-
-struct vexb_dspmat {
-    int dev = 0, part = 0, nparts = 1, val_dtype = VEXB_F64;
-    size_t nrows = 0, ncols_local = 0, n_ghost = 0, n_send = 0;
-    vexb_spmat *loc = nullptr;      // rows without ghost entries (all rows when there are no ghosts)
-    vexb_spmat *bnd = nullptr;      // local entries of the rows that also have ghost entries (row-compressed)
-    vexb_spmat *rem = nullptr;      // ghost entries of those rows (row-compressed)
-    int *send_cols = nullptr;       // device: local x indices to pack, grouped by destination
-    void *send_buf = nullptr;       // device: n_send values
-    void *ghost_buf = nullptr;      // device: n_ghost values ("rx" of spmat.hpp:273)
-    std::vector<size_t> send_counts, recv_counts;
-    cudaStream_t side = nullptr;    // secondary queue (spmat.hpp:81-82)
-    cudaEvent_t ev_pack = nullptr, ev_halo = nullptr, ev_x = nullptr;
-    // host copies of the split, kept for parity checks
-    std::vector<int64_t> loc_ptr, loc_col, rem_ptr, rem_col;
-    std::vector<char> loc_val, rem_val;
-    size_t loc_nnz = 0, rem_nnz = 0; bool split_kept = false;
-};
 
 namespace vexb {
 
@@ -55,6 +39,7 @@ extern "C" int vexb_dspmat_destroy(vexb_dspmat *A) {
     DeviceGuard g(A->dev);
     vexb_spmat_destroy(A->loc); vexb_spmat_destroy(A->bnd); vexb_spmat_destroy(A->rem);
     cudaFree(A->send_cols); cudaFree(A->send_buf); cudaFree(A->ghost_buf);
+    halo_link_destroy(A->halo);
     if (A->side) cudaStreamDestroy(A->side);
     if (A->ev_pack) cudaEventDestroy(A->ev_pack);
     if (A->ev_halo) cudaEventDestroy(A->ev_halo);
@@ -87,6 +72,11 @@ extern "C" int vexb_dspmat_create(int dev, void *stream, int part, const vexb_ha
     A->dev = dev; A->part = part; A->nparts = plan->nparts; A->val_dtype = val_dtype;
     A->nrows = nrows; A->ncols_local = col_end - col_begin; A->n_ghost = ghost.size();
     A->send_counts = plan->send_counts[part]; A->recv_counts = plan->recv_counts[part];
+    A->ghost_counts.resize(plan->nparts); A->land_off.assign(plan->nparts, 0);
+    for (int p = 0; p < plan->nparts; ++p) {
+        A->ghost_counts[p] = plan->ghost[p].size();
+        for (int q = 0; q < part; ++q) A->land_off[p] += plan->recv_counts[p][q];   // receives land in ascending source order
+    }
 
     // Split each row into local and remote entries, keeping storage order (csr.inl:92-112).
     std::vector<int> lrow(nrows + 1, 0), lcol; lcol.reserve((size_t)nnz);
@@ -154,9 +144,32 @@ extern "C" int vexb_dspmat_create(int dev, void *stream, int part, const vexb_ha
         } else {
             st = spmat_from_csr(dev, nrows, A->ncols_local, irow, icol, ival.data(), val_dtype, fmt, &irids, &A->loc);
         }
+        if (st == VEXB_OK && plan->nparts <= VEXB_MAX_HALO_PARTS) {
+            // the same boundary rows once more, local and ghost entries together in storage order (column-major, one
+            // thread per row): what the fused peer-memory apply reads (distapply.cu).  col >= 0: local x index,
+            // col <= -2: ghost index -(col+2), -1: padding.
+            int wb = 0;
+            for (int i : bids) wb = std::max(wb, (lrow[i + 1] - lrow[i]) + (rrow_full[i + 1] - rrow_full[i]));
+            const size_t bp = (bids.size() + 15) / 16 * 16;
+            std::vector<int> mcol(bp * (size_t)wb, -1);
+            std::vector<char> mval(bp * (size_t)wb * vs, 0);
+            for (size_t k = 0; k < bids.size(); ++k) {
+                const size_t i = (size_t)bids[k];
+                const int64_t a = read_index(ptr, ptr_bytes, i) - p0, b = read_index(ptr, ptr_bytes, i + 1) - p0;
+                int jl = lrow[i], jr = rrow_full[i], slot = 0;
+                for (int64_t j = a; j < b; ++j, ++slot) {
+                    const int64_t c = read_index(col, col_bytes, (size_t)j);
+                    const bool local = (size_t)c >= col_begin && (size_t)c < col_end;
+                    mcol[k + bp * (size_t)slot] = local ? lcol[jl++] : -(rcol[jr++] + 2);
+                    memcpy(&mval[(k + bp * (size_t)slot) * vs], (const char *)val + (size_t)j * vs, vs);
+                }
+            }
+            st = halo_set_boundary(A, bids, wb, mcol, mval.data());
+        }
         if (st == VEXB_OK) st = spmat_from_csr(dev, nrows, A->ncols_local, brow, bcol, bval.data(), val_dtype, VEXB_FMT_CSR, &bids, &A->bnd);
         if (st == VEXB_OK) st = spmat_from_csr(dev, nrows, A->n_ghost, rrow, rcol, rval.data(), val_dtype, VEXB_FMT_CSR, &rids, &A->rem);
     }
+    if (st == VEXB_OK && plan->nparts <= VEXB_MAX_HALO_PARTS) st = halo_prepare(A);
     if (st != VEXB_OK) { vexb_dspmat_destroy(A); return st; }
 
     const std::vector<int64_t> &sc = plan->send_cols[part];
@@ -303,6 +316,14 @@ extern "C" int vexb_dspmat_apply(int nlocal, vexb_comm *const *comms, vexb_dspma
             VEXB_TRY(vexb_dspmat_mul_local(parts[k], streams ? streams[k] : nullptr, x[k], y[k], alpha, append));
         return VEXB_OK;
     }
+    // Peer-memory halo connected on every part (vexb_dspmat_halo_connect*): one fused launch per part, no NCCL, no copies.
+    bool peer_halo = !param("dspmat.no_peer_halo", 0);
+    for (int k = 0; peer_halo && k < nlocal; ++k) { int c = 0; vexb_dspmat_halo_connected(parts[k], &c); peer_halo = c != 0; }
+    if (peer_halo) {
+        for (int k = 0; k < nlocal; ++k)
+            VEXB_TRY(dist_apply(parts[k], (cudaStream_t)(streams ? streams[k] : nullptr), x[k], y[k], alpha, append, nullptr, nullptr, nullptr));
+        return VEXB_OK;
+    }
     std::vector<void *> side(nlocal);
     // 1. side stream (high priority): wait for x, gather what the neighbours need (spmat.hpp:127-135)
     for (int k = 0; k < nlocal; ++k) {
@@ -321,7 +342,7 @@ extern "C" int vexb_dspmat_apply(int nlocal, vexb_comm *const *comms, vexb_dspma
     for (int k = 0; k < nlocal; ++k)
         VEXB_TRY(vexb_spmv(parts[k]->dev, streams ? streams[k] : nullptr, parts[k]->loc, x[k], y[k], alpha, append));
     // 3. ... the halo over NVLink on the side streams (replaces spmat.hpp:149-176), then the boundary rows
-    if (!param("dspmat.debug_skip_exchange", 0)) VEXB_TRY(vexb_halo_exchange(nlocal, comms, parts, side.data()));
+    VEXB_TRY(vexb_halo_exchange(nlocal, comms, parts, side.data()));
     for (int k = 0; k < nlocal; ++k) {
         const vexb_dspmat *A = parts[k];
         cudaStream_t st = streams ? (cudaStream_t)streams[k] : nullptr;
@@ -331,5 +352,29 @@ extern "C" int vexb_dspmat_apply(int nlocal, vexb_comm *const *comms, vexb_dspma
         VEXB_CUDA(cudaEventRecord(A->ev_halo, A->side));
         VEXB_CUDA(cudaStreamWaitEvent(st, A->ev_halo, 0));
     }
+    return VEXB_OK;
+}
+
+// y (=|+=) alpha*A*x and, in the same launch, d_result = sum over ALL parts of dot_with . y_new (combined across the GPUs
+// of `peers` inside the kernel, every GPU ends with the same bits).  This is q = A p; (p, q) of a CG iteration as one
+// kernel per GPU (the reference fuses the product into a consumer kernel on one device: sparse/product.hpp:45-130,
+// spmat/inline_spmv.hpp:68-76; its multi-device SpMat needs a separate reduction).  Needs the peer-memory halo on every
+// part (or a single part) and a hybrid-ELL interior strip: otherwise VEXB_ERR_UNSUPPORTED and the caller composes it.
+extern "C" int vexb_dspmat_apply_dot(int nlocal, vexb_dspmat *const *parts, void *const *streams, const void *const *x,
+                                     void *const *y, double alpha, int append, const void *const *dot_with,
+                                     void *const *d_result, vexb_peer *const *peers) {
+    VEXB_CHECK(nlocal >= 1 && parts && x && y && dot_with && d_result, "bad arguments");
+    for (int k = 0; k < nlocal; ++k) {
+        VEXB_CHECK(parts[k] && dot_with[k] && d_result[k], "part %d: NULL argument", k);
+        int c = 0;
+        VEXB_TRY(vexb_dspmat_halo_connected(parts[k], &c));
+        const vexb_spmat *S = parts[k]->loc;
+        if (!c || !S || S->fmt != VEXB_FMT_HELL || S->nnz == 0 || param("dspmat.no_peer_halo", 0) || param("dspmat.no_fused_dot", 0))
+            VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "fused product + dot needs the peer-memory halo and a hybrid-ELL interior strip on every part");
+        VEXB_CHECK(parts[k]->nparts == 1 || (peers && peers[k]), "part %d: a peer group is needed to combine the dot across GPUs", k);
+    }
+    for (int k = 0; k < nlocal; ++k)
+        VEXB_TRY(dist_apply(parts[k], (cudaStream_t)(streams ? streams[k] : nullptr), x[k], y[k], alpha, append, dot_with[k], d_result[k],
+                            parts[k]->nparts > 1 ? peers[k] : nullptr));
     return VEXB_OK;
 }

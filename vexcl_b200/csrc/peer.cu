@@ -2,6 +2,7 @@
 // (include/vexb200.h, "Peer memory").  See peer.cuh for the protocol.
 #include "peer.cuh"
 #include <vector>
+#include <mutex>
 
 namespace vexb {
 
@@ -17,8 +18,9 @@ __global__ void peer_allreduce_kernel(PeerArgs pa, T *buf, int op) {
     __shared__ unsigned long long px[VEXB_MAX_PEERS], py[VEXB_MAX_PEERS];
     const unsigned long long v0 = bits_of<T>(buf[0]);
     const unsigned long long v1 = op == VEXB_MINMAX ? bits_of<T>(buf[1]) : 0ull;
-    peer_exchange(pa, v0, v1, px, py);
-    if (threadIdx.x == 0) {
+    const bool arrived = peer_exchange(pa, v0, v1, px, py);
+    if (threadIdx.x == 0 && !arrived) { buf[0] = peer_poison<T>(); if (op == VEXB_MINMAX) buf[1] = peer_poison<T>(); }
+    if (threadIdx.x == 0 && arrived) {
         T a = of_bits<T>(px[0]), b = of_bits<T>(py[0]);
         for (int r = 1; r < pa.nranks; ++r) {
             const T x = of_bits<T>(px[r]), y = of_bits<T>(py[r]);
@@ -34,7 +36,23 @@ __global__ void peer_allreduce_kernel(PeerArgs pa, T *buf, int op) {
     }
 }
 
+// One word per process, written by kernels of any device when a peer fails to arrive (pinned + mapped + portable:
+// with unified addressing the host pointer is valid on every device).
+unsigned long long *peer_fault_word() {
+    static std::mutex mx;
+    static unsigned long long *word = nullptr;
+    std::lock_guard<std::mutex> lock(mx);
+    if (!word) {
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, 64, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        memset(p, 0, 64);
+        word = (unsigned long long *)p;
+    }
+    return word;
+}
+
 static int alloc_mailbox(vexb_peer *P) {
+    P->fault_host = peer_fault_word();
     VEXB_CUDA(cudaMalloc((void **)&P->mailbox, kMailboxWords * 8));
     VEXB_CUDA(cudaMemset(P->mailbox, 0, kMailboxWords * 8));
     VEXB_CUDA(cudaDeviceSynchronize());
@@ -115,6 +133,14 @@ extern "C" int vexb_peer_error(vexb_peer *peer, unsigned long long *epoch_of_tim
     VEXB_CHECK(peer && epoch_of_timeout, "NULL argument");
     DeviceGuard g(peer->dev);
     VEXB_CUDA(cudaMemcpy(epoch_of_timeout, peer->mailbox + 1, 8, cudaMemcpyDeviceToHost));
+    return VEXB_OK;
+}
+
+extern "C" int vexb_peer_fault(unsigned long long *epoch, int clear) {
+    unsigned long long *w = peer_fault_word();
+    const unsigned long long v = w ? *(volatile unsigned long long *)w : 0ull;
+    if (epoch) *epoch = v;
+    if (clear && w) *(volatile unsigned long long *)w = 0ull;
     return VEXB_OK;
 }
 

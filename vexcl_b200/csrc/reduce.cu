@@ -117,11 +117,13 @@ __device__ __forceinline__ void block_finish(Fold<OP, T> f, void *ws, T *result,
     if (pa.nranks > 1) {
         // combine across GPUs in the same kernel: one-hop exchange over NVLink peer memory (peer.cuh)
         __shared__ unsigned long long px[VEXB_MAX_PEERS], py[VEXB_MAX_PEERS];
-        peer_exchange(pa, to_bits<T>(sx[0]), to_bits<T>(sy[0]), px, py);
+        const bool arrived = peer_exchange(pa, to_bits<T>(sx[0]), to_bits<T>(sy[0]), px, py);
         if (threadIdx.x == 0) {
-            Fold<OP, T> b; b.x = from_bits<T>(px[0]); b.y = from_bits<T>(py[0]);
-            for (int r = 1; r < pa.nranks; ++r) { Fold<OP, T> o; o.x = from_bits<T>(px[r]); o.y = from_bits<T>(py[r]); b.merge(o); }
-            sx[0] = b.x; sy[0] = b.y;
+            if (arrived) {
+                Fold<OP, T> b; b.x = from_bits<T>(px[0]); b.y = from_bits<T>(py[0]);
+                for (int r = 1; r < pa.nranks; ++r) { Fold<OP, T> o; o.x = from_bits<T>(px[r]); o.y = from_bits<T>(py[r]); b.merge(o); }
+                sx[0] = b.x; sy[0] = b.y;
+            } else { sx[0] = peer_poison<T>(); sy[0] = peer_poison<T>(); }   // a peer timed out: never a partial fold (peer.cuh)
         }
         __syncthreads();
     }
@@ -182,6 +184,101 @@ __global__ void __launch_bounds__(256) reduce_sweep_kernel(SweepArgs a, size_t n
 #pragma unroll
         for (int j = 0; j < E; ++j) if (u || j) f.merge(acc[u][j]);
     block_finish<OP, T>(f, ws, result, pa);
+}
+
+// ---- CG vector updates (BASELINE configs[4]: "fused CG step = SpMV + 2 axpy + 2 dot") ---------------------------------
+// After q = A p and (p, q) (one launch: vexb_dspmat_apply_dot) an iteration needs
+//     alpha = rho / (p, q);  r -= alpha q;  rho' = (r, r)                       <- cg_update_r_kernel, one sweep, 24 B/row
+//     beta = rho' / rho;     x += alpha p;  p = r + beta p                      <- cg_update_xp_kernel, one sweep, 40 B/row
+// The scalars stay in device memory (the divisions happen in the kernels), rho' is folded like any Reductor sum and
+// combined across GPUs through the peer mailboxes in the same kernel.  Same unfused arithmetic per element as the
+// composition x += alpha*p; r -= alpha*q; sum(r*r); p = r + beta*p through vexb_eval / vexb_reduce, 64 bytes per row
+// instead of 96 (x += alpha p is deferred to the sweep that rewrites p anyway: it needs the OLD p, which that sweep reads).
+template <class T, int U>
+__global__ void __launch_bounds__(256) cg_update_r_kernel(size_t n, T *r, const T *q, const T *rho, const T *pq,
+                                                           void *ws, T *rho_new, PeerArgs pa) {
+    typedef Lanes<T> L;
+    constexpr int E = L::E;
+    const T alpha = Arith<T>::div(*rho, *pq);
+    Fold<VEXB_SUM, T> acc[U][E];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < E; ++j) acc[u][j].init();
+    const size_t nvec = n / E;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < nvec; base += stride) {
+        Vec256 vr[U], vq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t iv = base + (size_t)u * blockDim.x;
+            if (iv < nvec) { vr[u] = ldg256((const char *)r + iv * 32); vq[u] = ldg256((const char *)q + iv * 32); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t iv = base + (size_t)u * blockDim.x;
+            if (iv < nvec) {
+                Vec256 orr;
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    const T rn = Arith<T>::sub(L::get(vr[u], j), Arith<T>::mul(alpha, L::get(vq[u], j)));
+                    L::set(orr, j, rn);
+                    acc[u][j].take(Arith<T>::mul(rn, rn));
+                }
+                stg256((char *)r + iv * 32, orr);
+            }
+        }
+    }
+    const size_t i = nvec * E + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const T rn = Arith<T>::sub(r[i], Arith<T>::mul(alpha, q[i]));
+        r[i] = rn;
+        acc[0][0].take(Arith<T>::mul(rn, rn));
+    }
+    Fold<VEXB_SUM, T> f = acc[0][0];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < E; ++j) if (u || j) f.merge(acc[u][j]);
+    block_finish<VEXB_SUM, T>(f, ws, rho_new, pa);
+}
+
+template <class T, int U>
+__global__ void __launch_bounds__(256) cg_update_xp_kernel(size_t n, T *x, T *p, const T *r, const T *rho, const T *pq, const T *rho_new) {
+    typedef Lanes<T> L;
+    constexpr int E = L::E;
+    const T alpha = Arith<T>::div(*rho, *pq);
+    const T beta = Arith<T>::div(*rho_new, *rho);
+    const size_t nvec = n / E;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < nvec; base += stride) {
+        Vec256 vx[U], vr[U], vp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t iv = base + (size_t)u * blockDim.x;
+            if (iv < nvec) { vx[u] = ldg256((const char *)x + iv * 32); vr[u] = ldg256((const char *)r + iv * 32); vp[u] = ldg256((const char *)p + iv * 32); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t iv = base + (size_t)u * blockDim.x;
+            if (iv < nvec) {
+                Vec256 ox, op;
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    const T pj = L::get(vp[u], j);
+                    L::set(ox, j, Arith<T>::add(L::get(vx[u], j), Arith<T>::mul(alpha, pj)));
+                    L::set(op, j, Arith<T>::add(L::get(vr[u], j), Arith<T>::mul(beta, pj)));
+                }
+                stg256((char *)x + iv * 32, ox); stg256((char *)p + iv * 32, op);
+            }
+        }
+    }
+    const size_t i = nvec * E + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const T pj = p[i];
+        x[i] = Arith<T>::add(x[i], Arith<T>::mul(alpha, pj));
+        p[i] = Arith<T>::add(r[i], Arith<T>::mul(beta, pj));
+    }
 }
 
 template <class T> __device__ __forceinline__ T v_as(V v);
@@ -354,5 +451,55 @@ extern "C" int vexb_reduce_fetch(int dev, void *stream, const void *d_result, in
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     VEXB_CUDA(cudaMemcpyAsync(host_out, d_result, dtype_size(dtype) * (size_t)count, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     VEXB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    // a kernel that gave up waiting for a peer GPU (fused combine, peer-memory halo) poisons its result and raises the
+    // process-wide fault: report it here instead of handing back a poisoned value as if it were a sum
+    unsigned long long fault = 0;
+    vexb_peer_fault(&fault, 0);
+    if (fault) VEXB_FAIL(VEXB_ERR_PEER, "a peer GPU did not arrive within the time limit (first seen at epoch %llu); results that needed it are NaN / all-ones", fault);
+    return VEXB_OK;
+}
+
+extern "C" int vexb_cg_update_r(int dev, void *stream, int dtype, size_t n, void *r, const void *q,
+                                const void *d_rho, const void *d_pq, void *d_rho_new, void *d_workspace, vexb_peer *peer) {
+    VEXB_CHECK(dtype == VEXB_F64 || dtype == VEXB_F32, "CG updates are defined for f64 / f32");
+    VEXB_CHECK(d_rho && d_pq && d_rho_new && d_workspace, "NULL scalar / workspace");
+    PeerArgs pa; memset(&pa, 0, sizeof(pa));
+    if (peer && peer->nranks > 1) { VEXB_CHECK(peer->dev == dev, "peer group lives on device %d, not %d", peer->dev, dev); pa = peer->args(); }
+    if (n == 0) {
+        VEXB_TRY(vexb_reduce_identity(dev, stream, dtype, VEXB_SUM, d_rho_new));
+        return pa.nranks > 1 ? vexb_peer_allreduce(peer, stream, d_rho_new, dtype, VEXB_SUM) : VEXB_OK;
+    }
+    VEXB_CHECK(r && q && aligned32(r) && aligned32(q), "vectors must be non-NULL and 32-byte aligned");
+    DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
+    long bps = param("reduce.blocks_per_sm", 8);
+    if (bps < 1) bps = 1; if (bps > kMaxBlocksPerSm) bps = kMaxBlocksPerSm;
+    const size_t cap = (size_t)sm_count(dev) * (size_t)bps;
+    const size_t E = dtype == VEXB_F64 ? 4 : 8;
+    size_t want = (n / E + 511) / 512; if (want < 1) want = 1;
+    const int blocks = (int)(want < cap ? want : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == VEXB_F64) cg_update_r_kernel<double, 2><<<blocks, 256, 0, st>>>(n, (double *)r, (const double *)q, (const double *)d_rho,
+                                (const double *)d_pq, d_workspace, (double *)d_rho_new, pa);
+    else cg_update_r_kernel<float, 2><<<blocks, 256, 0, st>>>(n, (float *)r, (const float *)q, (const float *)d_rho,
+                                (const float *)d_pq, d_workspace, (float *)d_rho_new, pa);
+    VEXB_LAUNCHED();
+    return VEXB_OK;
+}
+
+extern "C" int vexb_cg_update_xp(int dev, void *stream, int dtype, size_t n, void *x, void *p, const void *r,
+                                 const void *d_rho, const void *d_pq, const void *d_rho_new) {
+    VEXB_CHECK(dtype == VEXB_F64 || dtype == VEXB_F32, "CG updates are defined for f64 / f32");
+    VEXB_CHECK(d_rho && d_pq && d_rho_new, "NULL scalar");
+    if (n == 0) return VEXB_OK;
+    VEXB_CHECK(x && p && r && aligned32(x) && aligned32(p) && aligned32(r), "vectors must be non-NULL and 32-byte aligned");
+    DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
+    const size_t E = dtype == VEXB_F64 ? 4 : 8;
+    size_t want = (n / E + 255) / 256; if (want < 1) want = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == VEXB_F64) cg_update_xp_kernel<double, 1><<<(unsigned)want, 256, 0, st>>>(n, (double *)x, (double *)p, (const double *)r,
+                                (const double *)d_rho, (const double *)d_pq, (const double *)d_rho_new);
+    else cg_update_xp_kernel<float, 1><<<(unsigned)want, 256, 0, st>>>(n, (float *)x, (float *)p, (const float *)r,
+                                (const float *)d_rho, (const float *)d_pq, (const float *)d_rho_new);
+    VEXB_LAUNCHED();
     return VEXB_OK;
 }

@@ -11,6 +11,9 @@ struct vexb_spmat {
     // CSR stream
     void *val = nullptr; int *col = nullptr; int *rowptr = nullptr; int2 *tile = nullptr;
     size_t n_tiles = 0, tile_nnz = 0, tile_rows = 0;
+    int2 *wtile = nullptr; size_t n_wtiles = 0;   // warp tiles (<= 256 nnz, <= 256 rows) for csr_warp_kernel
+    int csr_variant = 0;                          // kernel picked for this strip when spmv.kernel is not set (see build())
+    size_t max_row_nnz = 0;
     // HELL
     size_t ell_width = 0, ell_pitch = 0, tail_nnz = 0;
     int *ell_col = nullptr; void *ell_val = nullptr;

@@ -24,6 +24,7 @@
 // columns, and unrolls the ELL loop for the common small widths.
 #include "spmat.hpp"
 #include "ccsr.hpp"
+#include "spmv_dev.cuh"
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -31,59 +32,6 @@
 
 
 namespace vexb {
-
-template <class T> __device__ __forceinline__ T t_mul(T a, T b);
-template <> __device__ __forceinline__ double t_mul<double>(double a, double b) { return __dmul_rn(a, b); }
-template <> __device__ __forceinline__ float t_mul<float>(float a, float b) { return __fmul_rn(a, b); }
-template <class T> __device__ __forceinline__ T t_add(T a, T b);
-template <> __device__ __forceinline__ double t_add<double>(double a, double b) { return __dadd_rn(a, b); }
-template <> __device__ __forceinline__ float t_add<float>(float a, float b) { return __fadd_rn(a, b); }
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// L2 residency control.  The matrix streams through once per product, x is gathered ~nnz/ncols
-// times: matrix traffic is marked evict-first and x evict-last, so the stream does not push x out
-// of the 126 MB L2 (x gathers that miss L1 then cost an L2 hit, not an HBM round trip).
-__device__ __forceinline__ uint64_t l2_policy_stream() {
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_keep() {
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
-
-__device__ __forceinline__ double ldg_keep(const double *p, uint64_t policy) {
-    double v; asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy)); return v;
-}
-__device__ __forceinline__ float ldg_keep(const float *p, uint64_t policy) {
-    float v; asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy)); return v;
-}
-__device__ __forceinline__ int ldg_stream(const int *p, uint64_t policy) {
-    int v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy)); return v;
-}
-__device__ __forceinline__ short ldg_stream(const short *p, uint64_t policy) {
-    short v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(policy)); return v;
-}
-// Column of an ELL slot.  32-bit storage holds it directly (-1 = padding); 16-bit storage (spmv.col16) holds its
-// distance from (row + shift), with -32768 = padding: 2 bytes less HBM traffic per stored entry for banded matrices.
-__device__ __forceinline__ int ell_column(int raw, size_t, int) { return raw; }
-__device__ __forceinline__ int ell_column(short raw, size_t row, int shift) { return raw == (short)-32768 ? -1 : (int)row + shift + (int)raw; }
-__device__ __forceinline__ double ldg_stream(const double *p, uint64_t policy) {
-    double v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy)); return v;
-}
-__device__ __forceinline__ float ldg_stream(const float *p, uint64_t policy) {
-    float v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy)); return v;
-}
-
-template <class T>
-__device__ __forceinline__ void store_y(T *y, size_t r, T sum, T alpha, int append) {
-    const T v = t_mul<T>(alpha, sum);
-    y[r] = append ? t_add<T>(y[r], v) : v;
-}
 
 // Phase A of the stream kernels: val_s[j] *= x[col_s[j]] for j in [lo, lo+cnt), all threads.
 // The gathers of a batch are issued before any product is stored, so a thread keeps UA
@@ -423,28 +371,8 @@ __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w
                                                     const int *__restrict__ row_ids) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    T sum = T(0);
     const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
-    if (W > 0) {
-        int c[W > 0 ? W : 1]; T v[W > 0 ? W : 1]; T xv[W > 0 ? W : 1];
-#pragma unroll
-        for (int j = 0; j < W; ++j) { c[j] = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
-#pragma unroll
-        for (int j = 0; j < W; ++j) xv[j] = (c[j] != -1) ? ldg_keep(x + c[j], keep) : T(0);
-#pragma unroll
-        for (int j = 0; j < W; ++j) if (c[j] != -1) sum = t_add<T>(sum, t_mul<T>(v[j], xv[j]));
-    } else {
-        // any width: plain dependent loop.  Measured faster on irregular matrices than batching 4 columns
-        // (4.2 vs 3.3 TB/s effective at average width 12): occupancy hides the latency, and a padded slot
-        // (column -1) costs 4 bytes, not 12, because its value is never fetched.
-        for (int j = 0; j < w_dyn; ++j) {
-            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift);
-            if (c != -1) sum = t_add<T>(sum, t_mul<T>(ldg_stream(ell_val + i + (size_t)j * pitch, stream), ldg_keep(x + c, keep)));
-        }
-    }
-    if (tail_ptr) {
-        for (int j = tail_ptr[i], e = tail_ptr[i + 1]; j < e; ++j) sum = t_add<T>(sum, t_mul<T>(tail_val[j], __ldg(x + tail_col[j])));
-    }
+    const T sum = hell_row_sum<T, W, C>(i, pitch, w_dyn, ell_col, shift, ell_val, tail_ptr, tail_col, tail_val, x, stream, keep);
     store_y<T>(y, row_ids ? (size_t)row_ids[i] : i, sum, alpha, append);
 }
 
@@ -471,6 +399,95 @@ __global__ void __launch_bounds__(256) csr_scalar_kernel(size_t n, const int *__
     }
     for (; j < e; ++j) sum = t_add<T>(sum, t_mul<T>(val[j], __ldg(x + col[j])));
     store_y<T>(y, row_ids ? (size_t)row_ids[r] : r, sum, alpha, append);
+}
+
+// ---- warp tiles (spmv.kernel = 4) --------------------------------------------------------------------------------
+// The row-block stream kernel again, but the unit of work is a WARP, not a CTA: rows are cut on the host into tiles of
+// <= 256 nonzeros (8 per lane) and <= 256 rows; a warp loads its tile's col/val with coalesced 4/8-byte loads straight
+// into registers (L1 no-allocate, L2 evict-first), gathers x (L2 evict-last), parks the products in its private 2 KB of
+// shared memory and sums rows from there -- in storage order by one lane per row (short rows: same bits as the reference
+// loop, csr.inl:163-170) or by groups of 4 / 8 / 32 lanes with a shuffle tree (longer rows).  There is no CTA-wide
+// barrier and no mbarrier: warps drift apart, so the loads of one overlap the gathers and row sums of the others (the
+// one-shot CTA kernel serialises load -> wait -> gather -> sum per CTA and reaches 0.74 of the HBM roofline; see
+// profiles/r01_ncu_csr_stream.md).  Warps are persistent and fetch the NEXT tile's descriptor while working on the
+// current one, so the col/val loads never wait on a dependent descriptor load.
+constexpr int kWarpTileNnz = 256;
+constexpr int kWarpTileRows = 256;
+constexpr int kWarpPer = kWarpTileNnz / 32;
+
+template <class T, int G>
+__device__ __forceinline__ void warp_rows(const T *prod, const int *__restrict__ rowptr, int r0, int nr, int j0, int lane,
+                                          T *y, T alpha, int append, const int *__restrict__ row_ids) {
+    // groups of G lanes per row; G == 1: one lane per row, storage order
+    constexpr int RPW = 32 / G;                       // rows per warp pass
+    const int sub = lane % G, grp = lane / G;
+    for (int rb = 0; rb < nr; rb += RPW) {
+        const int r = rb + grp;
+        T s = T(0);
+        if (r < nr) {
+            const int a = __ldg(rowptr + r0 + r) - j0, b = __ldg(rowptr + r0 + r + 1) - j0;
+            for (int j = a + sub; j < b; j += G) s = t_add<T>(s, prod[j]);
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) s = t_add<T>(s, __shfl_down_sync(0xffffffffu, s, off, G));
+        }
+        if (r < nr && sub == 0) store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, s, alpha, append);
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256, 4) csr_warp_kernel(const int2 *__restrict__ tile, int n_tiles, const int *__restrict__ rowptr,
+                                                           const int *__restrict__ col, const T *__restrict__ val,
+                                                           const T *__restrict__ x, T *y, T alpha, int append,
+                                                           const int *__restrict__ row_ids) {
+    __shared__ T prod_all[8][kWarpTileNnz];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T *prod = prod_all[warp];
+    const int total_warps = gridDim.x * 8;
+    int t = blockIdx.x * 8 + warp;
+    if (t >= n_tiles) return;
+    const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
+    int2 d0 = __ldg(tile + t), d1 = __ldg(tile + t + 1);
+    while (true) {
+        const int tn = t + total_warps;
+        int2 n0 = d0, n1 = d1;
+        if (tn < n_tiles) { n0 = __ldg(tile + tn); n1 = __ldg(tile + tn + 1); }        // next descriptor: in flight during this tile
+        const int r0 = d0.x, nr = d1.x - d0.x, j0 = d0.y, cnt = d1.y - d0.y;
+        if (cnt > kWarpTileNnz) {
+            // one long row: the warp strides over it
+            T s = T(0);
+            for (int j = j0 + lane; j < j0 + cnt; j += 32) s = t_add<T>(s, t_mul<T>(ldg_stream(val + j, stream), ldg_keep(x + ldg_stream(col + j, stream), keep)));
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s = t_add<T>(s, __shfl_down_sync(0xffffffffu, s, off));
+            if (lane == 0) store_y<T>(y, row_ids ? (size_t)row_ids[r0] : (size_t)r0, s, alpha, append);
+        } else if (nr > 0) {
+            int c[kWarpPer]; T v[kWarpPer];
+#pragma unroll
+            for (int k = 0; k < kWarpPer; ++k) {
+                const int j = lane + 32 * k;
+                if (j < cnt) { c[k] = ldg_stream(col + j0 + j, stream); v[k] = ldg_stream(val + j0 + j, stream); }
+            }
+#pragma unroll
+            for (int k = 0; k < kWarpPer; ++k) {
+                const int j = lane + 32 * k;
+                if (j < cnt) v[k] = t_mul<T>(v[k], ldg_keep(x + c[k], keep));
+            }
+#pragma unroll
+            for (int k = 0; k < kWarpPer; ++k) {
+                const int j = lane + 32 * k;
+                if (j < cnt) prod[j] = v[k];
+            }
+            __syncwarp();
+            if (cnt <= 6 * nr)        warp_rows<T, 1>(prod, rowptr, r0, nr, j0, lane, y, alpha, append, row_ids);
+            else if (cnt <= 24 * nr)  warp_rows<T, 4>(prod, rowptr, r0, nr, j0, lane, y, alpha, append, row_ids);
+            else if (cnt <= 64 * nr)  warp_rows<T, 8>(prod, rowptr, r0, nr, j0, lane, y, alpha, append, row_ids);
+            else                      warp_rows<T, 32>(prod, rowptr, r0, nr, j0, lane, y, alpha, append, row_ids);
+            __syncwarp();
+        }
+        if (tn >= n_tiles) break;
+        t = tn; d0 = n0; d1 = n1;
+    }
 }
 
 template <class T>
@@ -594,6 +611,26 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
         tiles.push_back(make_int2((int)n, rowptr[n]));
         A->n_tiles = tiles.size() - 1;
         VEXB_TRY(upload(tiles, 0, (void **)&A->tile, &A->device_bytes));
+        // warp tiles for csr_warp_kernel: <= 256 nnz and <= 256 rows, cut at row boundaries; a longer row is its own tile
+        std::vector<int2> wt;
+        size_t maxw = 0;
+        for (r = 0; r < n;) {
+            size_t e = r; const int j0 = rowptr[r];
+            while (e < n && e - r < (size_t)kWarpTileRows && rowptr[e + 1] - j0 <= kWarpTileNnz) ++e;
+            if (e == r) e = r + 1;
+            wt.push_back(make_int2((int)r, j0));
+            r = e;
+        }
+        wt.push_back(make_int2((int)n, rowptr[n]));
+        for (size_t i = 0; i < n; ++i) maxw = std::max(maxw, (size_t)(rowptr[i + 1] - rowptr[i]));
+        A->n_wtiles = wt.size() - 1; A->max_row_nnz = maxw;
+        VEXB_TRY(upload(wt, 0, (void **)&A->wtile, &A->device_bytes));
+        // Kernel for this strip unless spmv.kernel says otherwise.  Short, even rows (max <= 2 x mean, mean <= 16): one
+        // thread per row straight from the CSR arrays (csr_scalar_kernel) -- every lane always has loads in flight and the
+        // sectors a warp touches are used up within a few iterations (measured 0.98 of the HBM roofline on 5-point Poisson
+        // against 0.76 for the TMA tile kernel, profiles/r02_variant_probe.json).  Anything else: warp tiles.
+        const double mean = n ? (double)A->nnz / (double)n : 0.0;
+        A->csr_variant = (mean <= 16.0 && (double)maxw <= 2.0 * mean + 2.0) ? 3 : 4;
         VEXB_TRY(upload(rowptr, 16, (void **)&A->rowptr, &A->device_bytes));
         VEXB_TRY(upload(col, 16, (void **)&A->col, &A->device_bytes));
         VEXB_TRY(upload(val, 16, &A->val, &A->device_bytes));
@@ -613,11 +650,12 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
             tptr[i + 1] = (int)tcol.size();
         }
         A->tail_nnz = tcol.size();
-        VEXB_TRY(upload(ecol, 0, (void **)&A->ell_col, &A->device_bytes));
         VEXB_TRY(upload(eval, 0, &A->ell_val, &A->device_bytes));
-        if (param("spmv.col16", 0) && w > 0) {
+        if (param("spmv.col16", 1) && w > 0) {
             // Banded matrices: every stored column lies within +-32767 of (row + shift) for one shift per strip, so
-            // the ELL columns fit 16 bits.  The kernel then streams 10 instead of 12 bytes per stored entry.
+            // the ELL columns fit 16 bits.  The kernel then streams 10 instead of 12 bytes per stored entry
+            // (measured on configs[2]: 0.098 ms against 0.110 ms per product, profiles/r02_variant_probe.json); same
+            // bits in y, only the index encoding differs.  spmv.col16 = 0 keeps 32-bit columns.
             long long lo = 0, hi = 0; bool any = false;
             for (size_t k = 0; k < w; ++k)
                 for (size_t i = 0; i < n; ++i) {
@@ -638,6 +676,7 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
                 VEXB_TRY(upload(e16, 0, (void **)&A->ell_col16, &A->device_bytes));
             }
         }
+        if (!A->ell_col16) VEXB_TRY(upload(ecol, 0, (void **)&A->ell_col, &A->device_bytes));
         if (A->tail_nnz) {
             VEXB_TRY(upload(tptr, 0, (void **)&A->tail_ptr, &A->device_bytes));
             VEXB_TRY(upload(tcol, 0, (void **)&A->tail_col, &A->device_bytes));
@@ -660,9 +699,24 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
         return VEXB_OK;
     }
     if (A->fmt == VEXB_FMT_PATTERNS) return vexb_ccsr_spmv(A->dev, (void *)st, A->patterns, x, y, (double)alpha, append);
-    // spmv.kernel: 0 = TMA-staged one-shot tiles, 1 = persistent TMA pipeline, 2 = register-staged tiles, 3 = thread per row
-    const long variant = param("spmv.kernel", param("spmv.pipeline", 0) ? 1 : 0);
-    if (A->fmt == VEXB_FMT_CSR && variant == 3) {
+    // spmv.kernel: 0 = TMA-staged one-shot CTA tiles, 1 = persistent TMA pipeline, 2 = register-staged CTA tiles, 3 = thread per row,
+    //              4 = warp tiles; unset (-1) = the strip's own choice (build(): 3 for short even rows, else 4)
+    long variant = param("spmv.kernel", param("spmv.pipeline", 0) ? 1 : -1);
+    if (variant < 0) variant = A->csr_variant;
+    if (A->fmt == VEXB_FMT_CSR && variant == 4) {
+        static std::atomic<int> per_sm[2];
+        const int ti = sizeof(T) == 8 ? 0 : 1;
+        if (!per_sm[ti].load()) {
+            int v = 0;
+            VEXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, csr_warp_kernel<T>, 256, 0));
+            per_sm[ti].store(v > 0 ? v : 1);
+        }
+        const long cap = param("spmv.ctas_per_sm", 0);
+        const size_t resident = (size_t)(cap > 0 && cap < per_sm[ti].load() ? cap : per_sm[ti].load()) * (size_t)sm_count(A->dev);
+        const size_t grid = std::min((A->n_wtiles + 7) / 8, resident);
+        csr_warp_kernel<T><<<(unsigned)grid, 256, 0, st>>>(A->wtile, (int)A->n_wtiles, A->rowptr, A->col, (const T *)A->val, x, y, alpha, append, A->row_ids);
+        VEXB_LAUNCHED();
+    } else if (A->fmt == VEXB_FMT_CSR && variant == 3) {
         csr_scalar_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, A->rowptr, A->col, (const T *)A->val, x, y, alpha, append, A->row_ids);
         VEXB_LAUNCHED();
     } else if (A->fmt == VEXB_FMT_CSR && variant == 2 && A->tile_nnz <= (size_t)kDirectThreads * kDirectPerThread) {
@@ -781,7 +835,7 @@ extern "C" int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols
 extern "C" int vexb_spmat_destroy(vexb_spmat *A) {
     if (!A) return VEXB_OK;
     DeviceGuard g(A->dev);
-    cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile);
+    cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile); cudaFree(A->wtile);
     vexb_ccsr_destroy(A->patterns);
     cudaFree(A->row_ids); cudaFree(A->ell_col); cudaFree(A->ell_col16); cudaFree(A->ell_val); cudaFree(A->tail_ptr); cudaFree(A->tail_col); cudaFree(A->tail_val);
     delete A;
@@ -836,7 +890,17 @@ extern "C" int vexb_spmat_hell_download(const vexb_spmat *A, int32_t *ell_col, v
     VEXB_CHECK(A && A->fmt == VEXB_FMT_HELL, "not a HELL matrix");
     DeviceGuard g(A->dev);
     const size_t vs = dtype_size(A->val_dtype), ne = A->ell_pitch * A->ell_width;
-    if (ell_col && ne) VEXB_CUDA(cudaMemcpy(ell_col, A->ell_col, ne * 4, cudaMemcpyDeviceToHost));
+    if (ell_col && ne && A->ell_col) VEXB_CUDA(cudaMemcpy(ell_col, A->ell_col, ne * 4, cudaMemcpyDeviceToHost));
+    if (ell_col && ne && !A->ell_col) {
+        // 16-bit storage: decode back to the reference's layout (column, or -1 for padding)
+        std::vector<short> e16(ne);
+        VEXB_CUDA(cudaMemcpy(e16.data(), A->ell_col16, ne * 2, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < A->ell_width; ++k)
+            for (size_t i = 0; i < A->ell_pitch; ++i) {
+                const short raw = e16[i + A->ell_pitch * k];
+                ell_col[i + A->ell_pitch * k] = raw == (short)-32768 ? -1 : (int32_t)((long long)i + A->ell_shift + raw);
+            }
+    }
     if (ell_val && ne) VEXB_CUDA(cudaMemcpy(ell_val, A->ell_val, ne * vs, cudaMemcpyDeviceToHost));
     if (csr_ptr) {
         if (A->tail_nnz) {

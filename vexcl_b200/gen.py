@@ -20,8 +20,11 @@ def poisson_dims(dim: int, nx: int, ny: int | None = None, nz: int | None = None
 
 
 def poisson_strip(dim: int, nx: int, ny: int | None = None, nz: int | None = None, r0: int = 0, r1: int | None = None,
-                  index_dtype=np.int64):
-    """Rows [r0, r1) of the Poisson matrix on an nx*ny(*nz) grid.  Returns (row, col, val)."""
+                  index_dtype=np.int64, spd: bool = False):
+    """Rows [r0, r1) of the Poisson matrix on an nx*ny(*nz) grid.  Returns (row, col, val).
+    spd=True: the symmetric positive definite form instead of the benchmark's (every row carries the stencil, neighbours
+    outside the grid are dropped -- homogeneous Dirichlet conditions eliminated), entries scaled to O(1): what a CG
+    iteration needs to converge (the benchmark's identity boundary rows make the matrix non-symmetric)."""
     nx, ny, nz = poisson_dims(dim, nx, ny, nz)
     N = nx * ny * nz
     r1 = N if r1 is None else r1
@@ -29,6 +32,22 @@ def poisson_strip(dim: int, nx: int, ny: int | None = None, nz: int | None = Non
     i = idx % nx
     j = (idx // nx) % ny
     k = idx // (nx * ny)
+    if spd:
+        if dim == 2:
+            offs = [-nx, -1, 0, 1, nx]
+            ok = [j > 0, i > 0, np.ones(idx.size, bool), i < nx - 1, j < ny - 1]
+            vals = [-1.0, -1.0, 4.0, -1.0, -1.0]
+        else:
+            offs = [-nx * ny, -nx, -1, 0, 1, nx, nx * ny]
+            ok = [k > 0, j > 0, i > 0, np.ones(idx.size, bool), i < nx - 1, j < ny - 1, k < nz - 1]
+            vals = [-1.0, -1.0, -1.0, 6.0, -1.0, -1.0, -1.0]
+        keep = np.stack(ok, axis=1)                              # (rows, w) in ascending column order
+        width = keep.sum(axis=1)
+        row = np.zeros(idx.size + 1, dtype=np.int64)
+        np.cumsum(width, out=row[1:])
+        cols = idx[:, None] + np.asarray(offs, dtype=np.int64)[None, :]
+        valm = np.broadcast_to(np.asarray(vals)[None, :], keep.shape)
+        return row.astype(index_dtype), cols[keep].astype(index_dtype), np.ascontiguousarray(valm[keep])
     bnd = (i == 0) | (i == nx - 1) | (j == 0) | (j == ny - 1)
     if dim == 3:
         bnd |= (k == 0) | (k == nz - 1)
@@ -73,6 +92,22 @@ def poisson_ccsr(n: int, index_dtype=np.uint64, col_dtype=np.int32):
     bnd = edge[:, None, None] | edge[None, :, None] | edge[None, None, :]
     idx = np.where(bnd, 0, 1).astype(index_dtype).ravel()
     return idx, row, col, val
+
+
+def irregular_rows(n: int, lo: int = 0, hi: int = 32, seed: int = 1, index_dtype=np.int64):
+    """An irregular square matrix: row widths U[lo, hi), columns ascending within a row (random gaps of 1..63 starting
+    about half a row's span left of the diagonal, clipped to the matrix), values U[-0.5, 0.5).  Returns (row, col, val)."""
+    rng = np.random.default_rng(seed)
+    w = rng.integers(lo, hi, n)
+    row = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(w, out=row[1:])
+    nnz = int(row[-1])
+    gaps = rng.integers(1, 64, nnz)
+    run = np.cumsum(gaps)
+    start = np.repeat(run[row[:-1].clip(max=max(nnz - 1, 0))] - gaps[row[:-1].clip(max=max(nnz - 1, 0))], w) if nnz else np.empty(0, np.int64)
+    base = np.repeat(np.arange(n, dtype=np.int64) - 16 * w, w)
+    col = np.clip(base + (run - start), 0, n - 1)
+    return row.astype(index_dtype), col.astype(index_dtype), rng.random(nnz) - 0.5
 
 
 def ccsr_bytes(nrows: int, idx_bytes: int = 8) -> int:
