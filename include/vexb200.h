@@ -227,6 +227,11 @@ int vexb_function_register(const char *name, int ret_dtype, int nargs, const int
 /* Generated source and NVRTC build log of the kernel vexb_eval would JIT for this request (for inspection
  * and for tests on machines without a GPU: NVRTC needs no device).  Two-call pattern on *len. */
 int vexb_jit_source(int lhs_dtype, int assign_op, const vexb_expr *expr, char *buf, size_t *len, int compile);
+/* Expressions without a hand-written sweep are served by the pre-compiled interpreter while NVRTC builds a kernel
+ * specialised to the expression on a background thread (started at the first use of a new expression shape; tunable
+ * "eval.jit": 0 = interpreter only, 1 = compile synchronously, 2 = this, the default).  *pending = 1 while any such
+ * compilation is still running: benchmarks and tests wait on it to time / check the specialised kernel. */
+int vexb_jit_pending(int *pending);
 /* Which kernel vexb_eval would take for this request: writes a short
  * name ("sweep:muladd", "interp", "jit", ...) to buf. */
 int vexb_eval_path(int lhs_dtype, int assign_op, const vexb_expr *expr, char *buf, size_t buflen);
@@ -240,9 +245,17 @@ int vexb_eval_path(int lhs_dtype, int assign_op, const vexb_expr *expr, char *bu
  * Replaces reductor.hpp:327-410; the host fold :412-436 is replaced by
  * vexb_reduce_fetch (single device) or vexb_comm_allreduce (+ fetch).
  * ---------------------------------------------------------------------- */
+typedef struct vexb_peer vexb_peer;   /* a group of GPUs that write each other's memory; see "Peer memory" below */
 int vexb_reduce_workspace_bytes(int dev, size_t *bytes);
 int vexb_reduce(int dev, void *stream, const vexb_expr *expr, int dtype, size_t n,
                 size_t index_offset, int op, void *d_result, void *d_workspace);
+/* Several reductions of the SAME expression in one pass over memory: vex::CombineReductors<R...> (reductor.hpp:132-280).
+ * ops: nops <= VEXB_MAX_COMBINED of VEXB_SUM / VEXB_SUM_KAHAN / VEXB_MAX / VEXB_MIN; d_result receives nops values of
+ * `dtype` in that order; d_workspace must hold nops * vexb_reduce_workspace_bytes() zero-initialised bytes.  With a
+ * peer group every value is combined across the GPUs inside the kernel, as in vexb_reduce_all. */
+#define VEXB_MAX_COMBINED 16
+int vexb_reduce_multi(int dev, void *stream, const vexb_expr *expr, int dtype, size_t n, size_t index_offset,
+                      int nops, const int *ops, void *d_result, void *d_workspace, vexb_peer *peer);
 /* Fill d_result with the identity of `op` (reductor.hpp:55,87,111): used for empty slices. */
 int vexb_reduce_identity(int dev, void *stream, int dtype, int op, void *d_result);
 /* D2H of `count` values + stream sync. */
@@ -296,7 +309,6 @@ int vexb_graph_destroy(vexb_graph *graph);
  * it stores NaN / all-ones instead of a partial fold and raises a sticky fault
  * (vexb_peer_error, vexb_peer_fault) instead of hanging.
  * ---------------------------------------------------------------------- */
-typedef struct vexb_peer vexb_peer;
 #define VEXB_IPC_HANDLE_BYTES 64
 int vexb_peer_create(int dev, int rank, int nranks, vexb_peer **peer, void *handle64);
 int vexb_peer_connect(vexb_peer *peer, const void *handles /* nranks * 64 bytes, rank order */);
@@ -483,9 +495,19 @@ int vexb_dspmat_halo_disconnect(vexb_dspmat *A);   /* back to NCCL / copies (e.g
 int vexb_dspmat_apply(int nlocal, vexb_comm *const *comms, vexb_dspmat *const *parts, void *const *streams,
                       const void *const *x, void *const *y, double alpha, int append);
 
-/* The product and a dot product with its result in ONE launch per GPU: y (=|+=) alpha*A*x, then
- * d_result[k][0] = sum over all parts of dot_with . y (same bits on every GPU; combined through the peer group inside
- * the kernel).  With dot_with = x this is q = A*p, (p, q) of a CG iteration.  Needs the peer-memory halo on every part
+/* Several right-hand sides in one pass over the matrix: vex::SpMat * vex::multivector<T,N> (multivector.hpp;
+ * the reference multiplies component by component, operations.hpp:876-880).  Hybrid-ELL strips take groups of up to 4
+ * vectors per launch (columns and values loaded once, same per-component bits as vexb_spmv); anything else falls back to
+ * one product per vector.  vexb_dspmat_apply_multi: x[k * nrhs + r] / y[k * nrhs + r] = slice of component r on part k;
+ * parts with a halo multiply component by component. */
+int vexb_spmv_multi(int dev, void *stream, const vexb_spmat *A, int nrhs, const void *const *x, void *const *y,
+                    double alpha, int append);
+int vexb_dspmat_apply_multi(int nlocal, vexb_comm *const *comms, vexb_dspmat *const *parts, void *const *streams,
+                            int nrhs, const void *const *x, void *const *y, double alpha, int append);
+
+/* The product and a dot product with its result without re-reading the vectors: y (=|+=) alpha*A*x, and
+ * d_result[k][0] = sum over all parts of dot_with . y (same bits on every GPU).  The product kernel leaves one partial
+ * per block; a one-block second launch folds them and combines across the peer group.  With dot_with = x this is q = A*p, (p, q) of a CG iteration.  Needs the peer-memory halo on every part
  * (or a single part) and a hybrid-ELL interior strip; returns VEXB_ERR_UNSUPPORTED otherwise (compose apply + reduce). */
 int vexb_dspmat_apply_dot(int nlocal, vexb_dspmat *const *parts, void *const *streams, const void *const *x,
                           void *const *y, double alpha, int append, const void *const *dot_with,

@@ -22,7 +22,17 @@ struct SUM        { static const int op = VEXB_SUM; };
 struct SUM_Kahan  { static const int op = VEXB_SUM_KAHAN; };
 struct MAX        { static const int op = VEXB_MAX; };
 struct MIN        { static const int op = VEXB_MIN; };
-struct MIN_MAX    { static const int op = VEXB_MINMAX; };
+/// Combines several reduce operations over one expression (reductor.hpp:132-280): the expression is evaluated once per
+/// element and folded by every R (vexb_reduce_multi: one pass over memory).  Result: a CL-style vector with s[k] = R_k.
+template <class... R>
+struct CombineReductors {
+    static_assert(sizeof...(R) >= 1 && sizeof...(R) <= VEXB_MAX_COMBINED, "between 1 and 16 reductors can be combined");
+    static const int op = -1;
+    static const unsigned count = sizeof...(R);
+    static const int *ops() { static const int o[] = { R::op... }; return o; }
+};
+/// Combined MIN and MAX operation (reductor.hpp:277): the two-value kernel of vexb_reduce_all.
+typedef CombineReductors<MIN, MAX> MIN_MAX;
 
 namespace detail {
 
@@ -76,8 +86,14 @@ inline std::shared_ptr<peer_set> peer_group(const std::vector<backend::command_q
     return ps;
 }
 
-template <class T, class RDC> struct reduce_result { typedef T type; static T make(const T *v) { return v[0]; } };
-template <class T> struct reduce_result<T, MIN_MAX> { typedef vec2<T> type; static type make(const T *v) { type r; r.s[0] = v[0]; r.s[1] = v[1]; return r; } };
+template <class T, class RDC> struct reduce_result { typedef T type; static const unsigned count = 1; static T make(const T *v) { return v[0]; } };
+template <class T, class... R> struct reduce_result<T, CombineReductors<R...>> {
+    static const unsigned count = sizeof...(R);
+    typedef vecn<T, cl_fit_vec_size<sizeof...(R)>::value> type;
+    static type make(const T *v) { type r = type(); for (unsigned k = 0; k < count; ++k) r.s[k] = v[k]; return r; }
+};
+template <class RDC> struct is_min_max : std::false_type {};
+template <> struct is_min_max<CombineReductors<MIN, MAX>> : std::true_type {};
 
 template <class T> inline T host_fold(int op, T a, T b) {
     switch (op) { case VEXB_MAX: return a > b ? a : b; case VEXB_MIN: return a < b ? a : b; default: return a + b; }
@@ -99,9 +115,10 @@ class Reductor {
             for (unsigned d = 0; d < queue.size(); ++d) {
                 size_t bytes = 0;
                 VEXB_CHECKED(vexb_reduce_workspace_bytes(queue[d].ordinal(), &bytes));
+                bytes *= detail::reduce_result<ScalarType, RDC>::count;       // combined reductions: one workspace slice each
                 ws[d] = backend::device_vector<char>(queue[d], bytes);
                 VEXB_CHECKED(vexb_memset(queue[d].ordinal(), ws[d].raw(), 0, bytes, queue[d].raw()));
-                res[d] = backend::device_vector<ScalarType>(queue[d], 8);
+                res[d] = backend::device_vector<ScalarType>(queue[d], 16);
             }
         }
 
@@ -124,9 +141,12 @@ class Reductor {
             detail::expr_props p;
             p.comp = comp;
             expr.props(p);
-            const int op = RDC::op, dt = dtype_of<ScalarType>::value;
-            const int cnt = op == VEXB_MINMAX ? 2 : 1;
-            ScalarType out[2] = {identity(op == VEXB_MINMAX ? VEXB_MIN : op), identity(VEXB_MAX)};
+            const int dt = dtype_of<ScalarType>::value;
+            const bool combined = RDC::op < 0 && !detail::is_min_max<RDC>::value;
+            const int op = detail::is_min_max<RDC>::value ? VEXB_MINMAX : RDC::op;
+            const int cnt = static_cast<int>(detail::reduce_result<ScalarType, RDC>::count);
+            ScalarType out[16];
+            for (int k = 0; k < cnt; ++k) out[k] = identity(op_of(k));
             if (!p.sized || p.size == 0) return detail::reduce_result<ScalarType, RDC>::make(out);   // reductor.hpp:318-321
             if (p.part.empty()) p.part = vex::partition(p.size, queue);                                // :323-325
 
@@ -136,8 +156,11 @@ class Reductor {
             for (unsigned d = 0; d < queue.size(); ++d) {
                 detail::ir_builder b(d, comp);
                 expr.lower(b);
-                const int st = vexb_reduce_all(queue[d].ordinal(), queue[d].raw(), &b.e, dt, p.part_size(d), p.part_start(d),
-                                               op, res[d].raw(), ws[d].raw(), fused ? ps->peers[d] : nullptr);
+                const int st = combined
+                    ? vexb_reduce_multi(queue[d].ordinal(), queue[d].raw(), &b.e, dt, p.part_size(d), p.part_start(d), cnt, ops_of(),
+                                        res[d].raw(), ws[d].raw(), fused ? ps->peers[d] : nullptr)
+                    : vexb_reduce_all(queue[d].ordinal(), queue[d].raw(), &b.e, dt, p.part_size(d), p.part_start(d),
+                                      op, res[d].raw(), ws[d].raw(), fused ? ps->peers[d] : nullptr);
                 if (st == VEXB_ERR_UNSUPPORTED && d == 0) {
                     // the expression calls a user function: evaluate it into a temporary (NVRTC side path), reduce that
                     vex::vector<typename Expr::value_type> tmp(queue, p.size);
@@ -148,10 +171,12 @@ class Reductor {
                     // devices 0..d-1 have already launched and will wait for everybody in the kernel: keep the group in step
                     // (identity + the standalone combine on the devices that did not launch), then report the failure
                     const std::string why = vexb_last_error();
-                    for (unsigned e = d; e < queue.size(); ++e) {
-                        vexb_reduce_identity(queue[e].ordinal(), queue[e].raw(), dt, op, res[e].raw());
-                        vexb_peer_allreduce(ps->peers[e], queue[e].raw(), res[e].raw(), dt, op);
-                    }
+                    for (unsigned e = d; e < queue.size(); ++e)
+                        for (int k = 0; k < (combined ? cnt : 1); ++k) {
+                            ScalarType *rk = res[e].raw_ptr() + k;
+                            vexb_reduce_identity(queue[e].ordinal(), queue[e].raw(), dt, combined ? op_of(k) : op, rk);
+                            vexb_peer_allreduce(ps->peers[e], queue[e].raw(), rk, dt, combined ? op_of(k) : op);
+                        }
                     throw backend::error(st, why);
                 }
                 VEXB_CHECKED(st);
@@ -162,14 +187,20 @@ class Reductor {
             } else if (cs && !cs->comms.empty()) {
                 std::vector<void*> bufs, streams;
                 for (unsigned d = 0; d < queue.size(); ++d) { bufs.push_back(res[d].raw()); streams.push_back(queue[d].raw()); }
+                if (combined) {
+                    for (int k = 0; k < cnt; ++k) {
+                        std::vector<void*> bk;
+                        for (unsigned d = 0; d < queue.size(); ++d) bk.push_back(res[d].raw_ptr() + k);
+                        VEXB_CHECKED(vexb_comm_allreduce(static_cast<int>(queue.size()), cs->comms.data(), bk.data(), streams.data(), 1, dt, op_of(k)));
+                    }
+                } else
                 VEXB_CHECKED(vexb_comm_allreduce(static_cast<int>(queue.size()), cs->comms.data(), bufs.data(), streams.data(), 1, dt, op));
                 VEXB_CHECKED(vexb_reduce_fetch(queue[0].ordinal(), queue[0].raw(), res[0].raw(), dt, cnt, out));
             } else {
                 for (unsigned d = 0; d < queue.size(); ++d) {
-                    ScalarType v[2];
+                    ScalarType v[16];
                     VEXB_CHECKED(vexb_reduce_fetch(queue[d].ordinal(), queue[d].raw(), res[d].raw(), dt, cnt, v));
-                    if (op == VEXB_MINMAX) { out[0] = detail::host_fold(VEXB_MIN, out[0], v[0]); out[1] = detail::host_fold(VEXB_MAX, out[1], v[1]); }
-                    else out[0] = detail::host_fold(op, out[0], v[0]);
+                    for (int k = 0; k < cnt; ++k) out[k] = detail::host_fold(op_of(k), out[k], v[k]);
                 }
             }
             return detail::reduce_result<ScalarType, RDC>::make(out);
@@ -177,6 +208,12 @@ class Reductor {
         std::vector<backend::command_queue> queue;
         mutable std::vector<backend::device_vector<char>> ws;
         mutable std::vector<backend::device_vector<ScalarType>> res;
+
+        /// The reduction that produces component k of the result.
+        template <class R = RDC> static typename std::enable_if<(R::op >= 0), int>::type op_of(int) { return R::op; }
+        template <class R = RDC> static typename std::enable_if<(R::op < 0), int>::type op_of(int k) { return R::ops()[k]; }
+        template <class R = RDC> static typename std::enable_if<(R::op >= 0), const int*>::type ops_of() { return nullptr; }
+        template <class R = RDC> static typename std::enable_if<(R::op < 0), const int*>::type ops_of() { return R::ops(); }
 
         static ScalarType identity(int op) {                     // reductor.hpp:55, :87, :111
             switch (op) {

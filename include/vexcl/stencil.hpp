@@ -11,8 +11,8 @@
  * The convolution is libvexb200's stencil_kernel (csrc/stencil.cu); a user-defined operator is generated and compiled
  * by NVRTC at first use, as the reference generates its kernel per operator.  With several device slices the elements
  * a slice needs from its neighbours are copied device to device into a per-slice halo buffer before the launch (the
- * reference stages them through the host, stencil.hpp:86-150); like the reference, the exchange waits for the queues
- * on both sides.
+ * reference stages them through the host and finishes every queue twice, stencil.hpp:86-150); here the exchange is ordered
+ * by events between the queues and never waits on the host.
  */
 #include <algorithm>
 #include <initializer_list>
@@ -39,37 +39,66 @@ class stencil_halos {
         }
 
         /// Fills left[d] / right[d] with the halo pointers of every slice that is not at an end of the vector.
+        /// Ordering is by events, nothing waits on the host (the reference finishes every queue twice, stencil.hpp:113,:147):
+        /// a slice's copies wait for the event "x complete" of the queues they read from, and every queue that was read
+        /// from waits -- on the device -- for the readers' "copies done" events before it runs anything later.
         void exchange_halos(const vex::vector<T> &x, std::vector<const T*> &left, std::vector<const T*> &right) const {
             precondition(x.nparts() == queue.size(), "stencil: the vector lives on other queues");
             if (queue.size() <= 1 || width <= 1) return;                          // stencil.hpp:89
             const size_t n = x.size();
-            for (auto &q : queue) q.finish();                                     // the neighbours' slices must be complete
-            for (unsigned d = 0; d < queue.size(); ++d) {
+            const unsigned nd = static_cast<unsigned>(queue.size());
+            if (ready.empty()) {
+                ready.assign(nd, nullptr); done.assign(nd, nullptr);
+                for (unsigned d = 0; d < nd; ++d) {
+                    VEXB_CHECKED(vexb_event_create(queue[d].ordinal(), &ready[d]));
+                    VEXB_CHECKED(vexb_event_create(queue[d].ordinal(), &done[d]));
+                }
+            }
+            for (unsigned d = 0; d < nd; ++d) VEXB_CHECKED(vexb_event_record(queue[d].ordinal(), ready[d], queue[d].raw()));
+            std::vector<std::vector<char>> reads(nd, std::vector<char>(nd, 0));   // reads[d][p]: slice d copied from slice p
+            for (unsigned d = 0; d < nd; ++d) {
                 const size_t start = x.part_start(d), size = x.part_size(d);
                 if (!size) continue;
                 if (start > 0 && lhalo > 0) {
                     const size_t have = std::min<size_t>(start, lhalo);           // elements that exist before this slice
                     if (have < static_cast<size_t>(lhalo)) fill(d, 0, lhalo - have, x[0]);
-                    gather(x, d, lhalo - have, start - have, start);
+                    gather(x, d, lhalo - have, start - have, start, reads[d]);
                     left[d] = dbuf[d].raw_ptr();
                 }
                 if (start + size < n && rhalo > 0) {
                     const size_t g0 = start + size, g1 = std::min(g0 + rhalo, n);
-                    gather(x, d, lhalo, g0, g1);
+                    gather(x, d, lhalo, g0, g1, reads[d]);
                     if (g1 - g0 < static_cast<size_t>(rhalo)) fill(d, lhalo + (g1 - g0), rhalo - (g1 - g0), x[n - 1]);
                     right[d] = dbuf[d].raw_ptr() + lhalo;
                 }
             }
-            for (auto &q : queue) q.finish();                                     // nobody overwrites x while a neighbour copies from it
+            // nobody overwrites x while a neighbour still copies from it
+            for (unsigned d = 0; d < nd; ++d) {
+                bool any = false;
+                for (unsigned p = 0; p < nd; ++p) any = any || reads[d][p];
+                if (any) VEXB_CHECKED(vexb_event_record(queue[d].ordinal(), done[d], queue[d].raw()));
+            }
+            for (unsigned d = 0; d < nd; ++d)
+                for (unsigned p = 0; p < nd; ++p)
+                    if (p != d && reads[d][p]) VEXB_CHECKED(vexb_stream_wait_event(queue[p].ordinal(), queue[p].raw(), done[d]));
         }
+        ~stencil_halos() {
+            for (unsigned d = 0; d < ready.size(); ++d) { vexb_event_destroy(queue[d].ordinal(), ready[d]); vexb_event_destroy(queue[d].ordinal(), done[d]); }
+        }
+        stencil_halos(const stencil_halos&) = delete;
+        stencil_halos& operator=(const stencil_halos&) = delete;
     private:
         /// Copy global elements [g0, g1) of x into dbuf[d] at element offset `at`.
-        void gather(const vex::vector<T> &x, unsigned d, size_t at, size_t g0, size_t g1) const {
+        mutable std::vector<void*> ready, done;      // per queue: "x complete" / "my copies of the neighbours' x are done"
+        void gather(const vex::vector<T> &x, unsigned d, size_t at, size_t g0, size_t g1, std::vector<char> &reads) const {
             for (unsigned p = 0; p < queue.size(); ++p) {
                 const size_t a = std::max(g0, x.part_start(p)), b = std::min(g1, x.part_start(p) + x.part_size(p));
-                if (a < b)
+                if (a < b) {
+                    if (p != d && !reads[p]) VEXB_CHECKED(vexb_stream_wait_event(queue[d].ordinal(), queue[d].raw(), ready[p]));
+                    reads[p] = 1;
                     VEXB_CHECKED(vexb_copy_peer(queue[d].ordinal(), dbuf[d].raw_ptr() + at + (a - g0), queue[p].ordinal(),
                                                 x(p).raw_ptr() + (a - x.part_start(p)), (b - a) * sizeof(T), queue[d].raw()));
+                }
             }
         }
         void fill(unsigned d, size_t at, size_t count, T value) const {

@@ -17,8 +17,11 @@ typedef unsigned long long cl_ulong;
 
 namespace vex {
 
-/// Two-component result of MIN_MAX (stands in for cl_double2 etc.; fields as in CL: s[0], s[1]).
-template <class T> struct vec2 { T s[2]; };
+/// N-component result of combined reductions (stands in for cl_double2 / cl_double4 / ...; fields as in CL: s[0], s[1], ...).
+template <class T, unsigned N> struct vecn { T s[N]; };
+template <class T> using vec2 = vecn<T, 2>;
+/// Smallest CL vector width that holds n components (vexcl/types.hpp cl_fit_vec_size): 1, 2, 4, 8 or 16.
+template <unsigned n> struct cl_fit_vec_size { static const unsigned value = n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : 16; };
 
 template <class T, class Enable = void> struct dtype_of;   // no definition: unsupported element type
 #define VEXB_DTYPE(T, code, nm) \

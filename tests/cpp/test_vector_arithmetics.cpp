@@ -62,6 +62,43 @@ BOOST_AUTO_TEST_CASE(reduce_expression)                 // :66-99
     BOOST_CHECK_EQUAL(max(fabs(X - X)), 0.0);
 }
 
+// vex::CombineReductors (vexcl/reductor.hpp:132-280): several reductions of one expression in a single pass
+BOOST_AUTO_TEST_CASE(combined_reductors)
+{
+    const size_t N = 100003;
+    std::vector<double> x = random_vector<double>(N);
+    for (auto &v : x) v = (v - 0.25) * 1e3;
+    vex::vector<double> X(ctx, x), Y(ctx, N);
+    Y = 2 * X;
+    const double lo = *std::min_element(x.begin(), x.end()), hi = *std::max_element(x.begin(), x.end());
+    double ks = 0, c = 0;
+    for (double v : x) { double y = v - c, t = ks + y; c = (t - ks) - y; ks = t; }
+    vex::Reductor<double, vex::CombineReductors<vex::MIN, vex::MAX, vex::SUM>> mms(ctx);
+    auto r = mms(X);                                                       // three components -> a 4-wide CL-style vector
+    static_assert(sizeof(r.s) == 4 * sizeof(double), "three reductors fit cl_double4");
+    BOOST_CHECK_EQUAL(r.s[0], lo);
+    BOOST_CHECK_EQUAL(r.s[1], hi);
+    BOOST_CHECK_CLOSE(r.s[2], ks, 1e-8);
+    vex::Reductor<double, vex::CombineReductors<vex::SUM, vex::SUM_Kahan, vex::MAX, vex::MIN, vex::MAX>> five(ctx);
+    auto q = five(X + Y);                                                  // an expression, five components -> 8-wide
+    static_assert(sizeof(q.s) == 8 * sizeof(double), "five reductors fit cl_double8");
+    BOOST_CHECK_CLOSE(q.s[0], 3 * ks, 1e-8);
+    BOOST_CHECK_CLOSE(q.s[1], 3 * ks, 1e-8);
+    BOOST_CHECK_EQUAL(q.s[2], 3 * hi);
+    BOOST_CHECK_EQUAL(q.s[3], 3 * lo);
+    BOOST_CHECK_EQUAL(q.s[4], 3 * hi);
+    vex::Reductor<int, vex::CombineReductors<vex::SUM, vex::MAX>> cnt(ctx);
+    auto k = cnt(X > 0.0);
+    size_t pos = 0; for (double v : x) pos += v > 0.0;
+    BOOST_CHECK_EQUAL(k.s[0], static_cast<int>(pos));
+    BOOST_CHECK_EQUAL(k.s[1], 1);
+    vex::vector<double> E(ctx, 0);                                         // empty: the initial values (reductor.hpp:318-321)
+    auto e = mms(E);
+    BOOST_CHECK_EQUAL(e.s[0], std::numeric_limits<double>::max());
+    BOOST_CHECK_EQUAL(e.s[1], std::numeric_limits<double>::lowest());
+    BOOST_CHECK_EQUAL(e.s[2], 0.0);
+}
+
 BOOST_AUTO_TEST_CASE(builtin_functions)                 // :101-111
 {
     const size_t N = 1024;

@@ -104,8 +104,9 @@ def test_product_with_fused_dot(ctx1):
 
 def test_fused_cg_matches_oracle(ctx1):
     ctx = ctx1
-    """CGFused: product + dot, r sweep + (r, r), x/p sweep -- three launches per iteration on one GPU; same history as the
-    oracle's composition, stream-launched and replayed as two alternating CUDA graphs."""
+    """CGFused: product with the dot partials in its epilogue (+ a one-block fold), r sweep + (r, r), x/p sweep -- four
+    launches per iteration and GPU; same history as the oracle's composition, stream-launched and replayed as two
+    alternating CUDA graphs."""
     from vexcl_b200.solvers import CGFused
     row, col, val, b, N = problem()
     iters = 25
@@ -132,4 +133,4 @@ def test_fused_cg_matches_oracle(ctx1):
         n0 = vx.launch_count()
         cg.step()
         if ctx.nparts == 1:
-            assert vx.launch_count() - n0 == 3             # the iteration IS three kernels
+            assert vx.launch_count() - n0 == 4             # product(+dot partials), fold, r sweep, x/p sweep

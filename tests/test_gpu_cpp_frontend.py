@@ -57,3 +57,21 @@ def test_cpp_stencil_two_slices(built):
         _run_stencil("2", 90)
     except subprocess.TimeoutExpired:
         pytest.fail("test_stencil with two slices did not finish in 90 s")
+
+
+def test_cpp_hotpath_benchmark(built):
+    """examples/hotpath_benchmark.cpp: the hot-path functions of the reference's examples/benchmark.cpp (saxpy :83-148,
+    vector :152-216, reductor :219-278, spmv :352-477) against include/vexcl, with the reference's own self-checks."""
+    import re
+    from vexcl_b200 import build
+    build.build_cpp_tests()
+    exe = BIN / "hotpath_benchmark"
+    assert exe.exists(), f"{exe} was not built"
+    r = subprocess.run([str(exe), "--quick"], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:]); print(r.stderr[-2000:])
+    assert r.returncode == 0
+    res = [float(v) for v in re.findall(r"res = ([-+0-9.eE]+|nan|inf)", r.stdout)]
+    assert len(res) == 4, r.stdout                               # saxpy, vector arithmetic, reduction, SpMV
+    assert res[0] <= 1e-12 and res[1] <= 1e-12 and res[3] <= 1e-12   # sums of squared differences against the CPU loops
+    assert res[2] <= 1e-10                                       # relative difference of the reductions
+    assert len(re.findall(r"Bandwidth:\s+[0-9.]+", r.stdout)) == 4

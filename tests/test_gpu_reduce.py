@@ -88,3 +88,23 @@ def test_empty_expression_returns_initial(ctx1):
     assert vx.Reductor(ctx1, np.float64, L.SUM)(x) == 0
     assert vx.Reductor(ctx1, np.float64, L.MAX)(x) == np.finfo(np.float64).min
     assert vx.Reductor(ctx1, np.float64, L.MIN)(x) == np.finfo(np.float64).max
+
+
+def test_combined_reductors(ctx):
+    """vex::CombineReductors<R...> (reductor.hpp:132-280): several reductions of one expression, one pass over memory."""
+    n = 250_007
+    X = (oracle.uniform_real(21, n) - 0.25) * 1e3
+    Y = oracle.uniform_real(22, n)
+    x, y = vx.vector(ctx, X), vx.vector(ctx, Y)
+    lo, hi, s = vx.Reductor(ctx, np.float64, [L.MIN, L.MAX, L.SUM])(x)
+    assert lo == X.min() and hi == X.max()
+    ref = oracle.kahan_sum(X)
+    assert abs(s - ref) <= 1e-10 * np.sum(np.abs(X))
+    r = vx.Reductor(ctx, np.float64, [L.SUM, L.SUM_KAHAN, L.MAX, L.MIN, L.MAX])(x * y + 1.0)
+    E = X * Y + 1.0
+    assert abs(r[0] - oracle.kahan_sum(E)) <= 1e-10 * np.sum(np.abs(E)) and abs(r[1] - oracle.kahan_sum(E)) <= 1e-10 * np.sum(np.abs(E))
+    assert r[2] == E.max() and r[3] == E.min() and r[4] == E.max()
+    cnt, any_ = vx.Reductor(ctx, np.int64, [L.SUM, L.MAX])(x > 0.0)
+    assert cnt == int((X > 0).sum()) and any_ == 1
+    for _ in range(3):                                           # the workspace slices are left reusable
+        assert vx.Reductor(ctx, np.float64, [L.MAX, L.MIN])(x) == (X.max(), X.min())

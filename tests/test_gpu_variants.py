@@ -117,3 +117,22 @@ def test_row_pattern_strips_match_the_oracle(built, ctx1, ctx2, ctx3, nparts):
             assert np.all(np.abs(y.read() - want) <= 1e-10 * oracle.csr_absrow(row, col, val, xh))
         y -= 0.5 * (A * x)
         assert np.all(np.abs(y.read() - 0.5 * want) <= 1e-10 * oracle.csr_absrow(row, col, val, xh))
+
+
+def test_row_patterns_on_a_rectangular_strip_with_rows_left_of_the_diagonal(ctx1):
+    """More rows than columns: rows i >= ncols whose entries all lie left of the diagonal, and empty rows, are valid CCSR
+    rows (the reach check used to start from the diagonal and rejected them)."""
+    n, m = 1000, 900
+    w = np.where(np.arange(n) >= 100, 2, 0)
+    row = np.concatenate([[0], np.cumsum(w)]).astype(np.int64)
+    i = np.arange(100, n)
+    col = np.stack([i - 100, np.minimum(i - 99, m - 1)], axis=1).ravel().astype(np.int64)
+    val = np.tile([2.0, -1.0], n - 100)
+    # the last row repeats column m-1 through the clamp: make it a separate pattern on purpose
+    xh = oracle.uniform_real(5, m)
+    A = vx.SpMat(ctx1, n, m, row, col, val, vx.FMT_PATTERNS)
+    assert A.info().loc.fmt == vx.FMT_PATTERNS and A.info().loc.n_tiles <= 3
+    x, y = vx.vector(ctx1, xh), vx.vector(ctx1, n)
+    y.assign(7.0)
+    y.assign(A * x)
+    assert np.array_equal(y.read(), oracle.csr_spmv(row, col, val, xh))

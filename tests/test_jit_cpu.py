@@ -148,3 +148,36 @@ def test_unregistered_call_is_rejected(env):
     buf = C.create_string_buffer(64)
     assert L.lib().vexb_eval_path(L.F64, L.SET, C.byref(e), buf, 64) == 2
     assert b"unregistered function" in L.lib().vexb_last_error()
+
+
+def test_compound_shifts_keep_the_type_of_the_left_operand(env):
+    """`a >>= b`: C/C++ (and the reference's emitted `lhs[i] >>= rhs`) shift in the promoted type of the LEFT operand; the
+    count's type does not matter.  With a signed a and an unsigned b the shift must stay arithmetic."""
+    vx, api, L, fake_vec = env
+    a, b = fake_vec(64, np.int32, 0x1000), fake_vec(64, np.uint32, 0x2000)
+    src = jit_source(api, L, a, L.RSH, b)
+    assert "lhs[i] = (int)((int)lhs[i] >> (int)" in src and "NVRTC: ok" in src
+    w = fake_vec(64, np.uint64, 0x3000)
+    src = jit_source(api, L, a, L.LSH, w)
+    assert "lhs[i] = (int)((int)lhs[i] << (int)" in src
+    # other compound operators still use the common type
+    src = jit_source(api, L, a, L.ADD, b)
+    assert "lhs[i] = (int)((unsigned int)lhs[i] + (unsigned int)" in src
+
+
+def test_sixteen_terminals_with_converted_scalars_normalise(env):
+    """8 vectors + 8 int literals used as doubles: the conversions of the scalars fold in place (no extra terminal slots),
+    so a full 16-terminal expression still fits (exprhost.hpp normalize_expr)."""
+    vx, api, L, fake_vec = env
+    vs = [fake_vec(256, np.float64, 0x1000 * (k + 1)) for k in range(8)]
+    e = vs[0] * 2
+    for k in range(1, 8):
+        e = e + vs[k] * (k + 2)                    # int scalars -> CVT to double
+    z = fake_vec(256, np.float64, 0x20000)
+    src = jit_source(api, L, z, L.SET, e, compile=False)
+    assert "vexb_jit_kernel" in src
+    # a scalar pushed twice with different conversions keeps both versions
+    s = api.Scalar(3)
+    i = fake_vec(256, np.int32, 0x30000)
+    src = jit_source(api, L, z, L.SET, (vs[0] * s) + (i * s), compile=False)
+    assert "vexb_jit_kernel" in src

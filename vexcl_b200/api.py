@@ -172,19 +172,22 @@ class Context:
 
     def use_stream(self, part: int, stream_ptr: int):
         """Run part `part` on an externally owned cudaStream_t (e.g. torch's current stream)."""
+        self.streams = dict(self.streams)                     # a new table: cached argument arrays notice the change
         self.streams[part] = C.c_void_p(stream_ptr)
 
-    def workspace(self, k: int):
-        if k not in self._ws:
+    def workspace(self, k: int, slices: int = 1):
+        """(reduction workspace, result buffer) of slot k; `slices` > 1: room for that many combined reductions."""
+        key = (k, slices) if slices > 1 else k
+        if key not in self._ws:
             lib = L.lib()
             nb = C.c_size_t()
             L.check(lib.vexb_reduce_workspace_bytes(self.devs[k], C.byref(nb)))
             ws, res = C.c_void_p(), C.c_void_p()
-            L.check(lib.vexb_malloc(self.devs[k], nb.value, C.byref(ws)))
-            L.check(lib.vexb_memset(self.devs[k], ws, 0, nb.value, self.streams[k]))
-            L.check(lib.vexb_malloc(self.devs[k], 64, C.byref(res)))
-            self._ws[k] = (ws, res)
-        return self._ws[k]
+            L.check(lib.vexb_malloc(self.devs[k], nb.value * slices, C.byref(ws)))
+            L.check(lib.vexb_memset(self.devs[k], ws, 0, nb.value * slices, self.streams[k]))
+            L.check(lib.vexb_malloc(self.devs[k], 128, C.byref(res)))
+            self._ws[key] = (ws, res)
+        return self._ws[key]
 
     def _arr(self, mapping):
         return (C.c_void_p * len(self.local))(*[mapping[k] for k in self.local])
@@ -527,6 +530,13 @@ class vector(Node):
         except Exception:
             pass
 
+    def _bufarr(self):
+        """The device pointers of the local slices as a C array (cached: the buffers live as long as the vector)."""
+        a = self.__dict__.get("_bufarr_c")
+        if a is None:
+            a = self._bufarr_c = self.ctx._arr(self.bufs)
+        return a
+
     def size(self): return self.n
     def nparts(self): return self.ctx.nparts
     def part_size(self, k): return int(self.part[k + 1] - self.part[k])
@@ -649,8 +659,51 @@ def check_peer_fault():
 class Reductor:
     """vex::Reductor<T, RDC> (reductor.hpp:289-439).  kind: L.SUM, L.SUM_KAHAN, L.MAX, L.MIN, L.MINMAX."""
 
-    def __init__(self, ctx: Context, dtype=np.float64, kind: int = L.SUM):
-        self.ctx, self.np_dtype, self.dtype, self.kind = ctx, np.dtype(dtype), _vdt(dtype), kind
+    def __init__(self, ctx: Context, dtype=np.float64, kind=L.SUM):
+        """kind: one of L.SUM, L.SUM_KAHAN, L.MAX, L.MIN, L.MINMAX -- or a sequence of the first four:
+        vex::CombineReductors<R...> (reductor.hpp:132-280), several reductions of one expression in one pass; the call
+        then returns a tuple."""
+        self.ctx, self.np_dtype, self.dtype = ctx, np.dtype(dtype), _vdt(dtype)
+        self.kinds = list(kind) if isinstance(kind, (list, tuple)) else None
+        self.kind = kind if self.kinds is None else None
+        if self.kinds is not None and not (1 <= len(self.kinds) <= 16 and all(k in (L.SUM, L.SUM_KAHAN, L.MAX, L.MIN) for k in self.kinds)):
+            raise ValueError("between 1 and 16 of SUM, SUM_KAHAN, MAX, MIN can be combined")
+
+    def _combined(self, expr, n, part):
+        """vexb_reduce_multi on every slot, then combine across slots (inside the kernel with a peer group)."""
+        lib, ctx, K = L.lib(), self.ctx, len(self.kinds)
+        ops = (C.c_int * K)(*self.kinds)
+        es = self.np_dtype.itemsize
+        fused = ctx.peers is not None and ctx.use_peer_reduce and ctx.nparts > 1
+        res = {}
+        for k in ctx.local:
+            ws, r = ctx.workspace(k, K)
+            low = _Lowering(k, int(part[k]))
+            low.lower(expr)
+            L.check(lib.vexb_reduce_multi(ctx.devs[k], ctx.streams[k], C.byref(low.e), self.dtype, int(part[k + 1] - part[k]), int(part[k]),
+                                          K, ops, r, ws, ctx.peers[k] if fused else None))
+            res[k] = r
+        out = np.empty(K, dtype=self.np_dtype)
+        k0 = ctx.local[0]
+        if ctx.nparts > 1 and not fused and ctx.comms is not None:
+            for j, op in enumerate(self.kinds):
+                bufs = {k: C.c_void_p(res[k].value + j * es) for k in ctx.local}
+                L.check(lib.vexb_comm_allreduce(len(ctx.local), ctx._arr(ctx.comms), ctx._arr(bufs), ctx._arr(ctx.streams), 1, self.dtype, op))
+        if ctx.nparts == 1 or fused or ctx.comms is not None:
+            L.check(lib.vexb_reduce_fetch(ctx.devs[k0], ctx.streams[k0], res[k0], self.dtype, K, out.ctypes.data))
+            return tuple(out)
+        if ctx.is_distributed:
+            raise RuntimeError("distributed context without a communicator")
+        acc = None
+        for k in ctx.local:                                        # device order, like reductor.hpp:420-436
+            L.check(lib.vexb_reduce_fetch(ctx.devs[k], ctx.streams[k], res[k], self.dtype, K, out.ctypes.data))
+            v = out.copy()
+            if acc is None:
+                acc = v
+            else:
+                for j, op in enumerate(self.kinds):
+                    acc[j] = acc[j] + v[j] if op in (L.SUM, L.SUM_KAHAN) else max(acc[j], v[j]) if op == L.MAX else min(acc[j], v[j])
+        return tuple(acc)
 
     def __call__(self, expr):
         lib = L.lib()
@@ -662,6 +715,8 @@ class Reductor:
         n = props[1]
         expr = _materialize_calls(ctx, expr, n)
         part = ctx.partition(n)
+        if self.kinds is not None:
+            return self._combined(expr, n, part)
         cnt = 2 if self.kind == L.MINMAX else 1
         res = {}
         for k in ctx.local:
@@ -822,15 +877,19 @@ class SpMat:
         ctx = self.ctx
         if x.n != self.m or y.n != self.n:
             raise ValueError("SpMat::apply: vector sizes do not match the matrix")
-        comms = ctx._arr(ctx.comms) if ctx.comms is not None else None
-        L.check(L.lib().vexb_dspmat_apply(len(ctx.local), comms, ctx._arr(self.parts), ctx._arr(ctx.streams),
-                                          ctx._arr(x.bufs), ctx._arr(y.bufs), float(alpha), int(append)))
+        fixed = self.__dict__.get("_apply_args")
+        if fixed is None or fixed[3] is not ctx.streams:          # the handle tables never change: build them once
+            fixed = self._apply_args = (len(ctx.local), ctx._arr(ctx.comms) if ctx.comms is not None else None, ctx._arr(self.parts),
+                                        ctx.streams, ctx._arr(ctx.streams), L.lib().vexb_dspmat_apply)
+        code = fixed[5](fixed[0], fixed[1], fixed[2], fixed[4], x._bufarr(), y._bufarr(), alpha, 1 if append else 0)
+        if code:
+            L.check(code)
         return y
 
 
 def _spmat_apply_dot(self, x: "vector", y: "vector", out: "DeviceScalar", dot_with: Optional["vector"] = None,
                      alpha: float = 1.0, append: bool = False) -> bool:
-    """y (=|+=) alpha*A*x and out = dot(dot_with or x, y) on every device.  One launch per GPU when the matrix has the
+    """y (=|+=) alpha*A*x and out = dot(dot_with or x, y) on every device.  The dot partials come out of the product kernel (plus a one-block fold launch) when the matrix has the
     peer-memory halo (or a single part) and a hybrid-ELL interior (vexb_dspmat_apply_dot); otherwise the product followed
     by a device-resident reduction.  Returns True when the fused kernel ran."""
     ctx, lib = self.ctx, L.lib()

@@ -287,13 +287,16 @@ int vexb::ccsr_create_ex(int dev, size_t n, size_t xlen, size_t m, const void *i
         hrow[k] = (int)r;
     }
     VEXB_CHECK(hrow[0] == 0, "CCSR row pointers must start at 0");
-    std::vector<long long> lo(m, 0), hi(m, 0);                   // reach of every unique row relative to the diagonal
+    // reach of every unique row relative to the diagonal, from its own entries only (an empty row reaches nothing; a row
+    // whose entries all lie left of the diagonal is fine for i >= xlen as long as i + hi stays inside x)
+    std::vector<long long> lo(m, 0), hi(m, 0);
     for (size_t u = 0; u < m; ++u)
         for (int j = hrow[u]; j < hrow[u + 1]; ++j) {
             const long long c = read_int(col, col_bytes, true, (size_t)j);
             VEXB_CHECK(c > -(1LL << 31) && c < (1LL << 31), "CCSR column offset does not fit 32 bits");
             hcol[(size_t)j] = (int)c;
-            lo[u] = c < lo[u] ? c : lo[u]; hi[u] = c > hi[u] ? c : hi[u];
+            if (j == hrow[u]) lo[u] = hi[u] = c;
+            else { lo[u] = c < lo[u] ? c : lo[u]; hi[u] = c > hi[u] ? c : hi[u]; }
         }
     auto *A = new vexb_ccsr();
     A->dev = dev; A->val_dtype = val_dtype; A->n = n; A->m = m; A->nnz = (size_t)nnz;
@@ -307,7 +310,7 @@ int vexb::ccsr_create_ex(int dev, size_t n, size_t xlen, size_t m, const void *i
         const long long u = read_int(idx, idx_bytes, false, i);
         if (!(u >= 0 && (size_t)u < m)) { delete A; VEXB_FAIL(VEXB_ERR_INVALID, "CCSR idx[%zu] = %lld names no unique row (m = %zu)", i, u, m); }
         // the reference reads x[i + col[j]] unchecked (ccsr.hpp:195); a matrix that reaches outside x is rejected here
-        if ((long long)i + lo[(size_t)u] < 0 || (long long)i + hi[(size_t)u] >= (long long)xlen) {
+        if (hrow[(size_t)u + 1] > hrow[(size_t)u] && ((long long)i + lo[(size_t)u] < 0 || (long long)i + hi[(size_t)u] >= (long long)xlen)) {
             delete A; VEXB_FAIL(VEXB_ERR_INVALID, "CCSR row %zu (unique row %lld) reaches outside the vector", i, u);
         }
         if (A->idx_bytes == 1) i8[i] = (uint8_t)u; else if (A->idx_bytes == 2) i16[i] = (uint16_t)u; else i32[i] = (int32_t)u;

@@ -21,9 +21,10 @@
 // that never shows up makes the waiters give up after ~20 s: they write NaN into the rows they could not compute and
 // raise the process-wide peer fault (vexb_peer_fault), instead of hanging or folding stale values.
 //
-// Optionally the kernel also accumulates dot(dot_with, y_new) over the rows it produces (block partials -> last block
-// folds them in a fixed order -> combine across GPUs through the reduction mailboxes of peer.cuh): the SpMV + dot(p, Ap)
-// step of a CG iteration in one launch (sparse/product.hpp:45-130 is the reference's fused form on one device).
+// Optionally the kernel also accumulates dot(dot_with, y_new) over the rows it produces: every block leaves one partial,
+// and a one-block second launch (dot_fold_kernel) folds them in a fixed order and combines the value across the GPUs
+// through the reduction mailboxes of peer.cuh.  That is q = A p and (p, q) of a CG iteration without re-reading p and q
+// (sparse/product.hpp:45-130 is the reference's fused form on one device).
 #include "dspmat.hpp"
 #include "spmv_dev.cuh"
 #include "peer.cuh"
@@ -89,9 +90,9 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
     }
 }
 
-// dot partials: [ticket][pad][partials...] in dot_ws (the Reductor workspace layout of reduce.cu is NOT shared: own buffer)
+// dot partials: one value per block in dot_ws (own buffer, not the Reductor workspace)
 template <class T, int W, class C, bool DOT>
-__global__ void __launch_bounds__(256) dist_apply_kernel(const __grid_constant__ DistArgs<T> a) {
+__global__ void __launch_bounds__(256, 8) dist_apply_kernel(const __grid_constant__ DistArgs<T> a) {
     unsigned long long *mine = a.box[a.rank];
     __shared__ unsigned long long s_epoch;
     __shared__ int s_ok;
@@ -201,18 +202,16 @@ __global__ void __launch_bounds__(256) dist_apply_kernel(const __grid_constant__
         }
     }
 
-    // ---- block epilogue: the epoch advances when the last halo block is done (they all read it at their start);
-    //      with DOT every block leaves a partial and the last block of the whole grid folds them ----
-    __shared__ T s_part[8];
-    __shared__ bool s_last;
-    if (!DOT) {
-        if (halo_block && threadIdx.x == 0) {
-            unsigned int *ticket = reinterpret_cast<unsigned int *>(mine + 2);
-            const unsigned int old = atomicAdd(ticket, 1u);
-            if (old == (unsigned)(a.n_push_blocks + a.n_bnd_blocks) - 1) { *ticket = 0; mine[0] = e; }
-        }
-        return;
+    // ---- block epilogue: the epoch advances when the last halo block is done (they all read it at their start); with
+    //      DOT every block leaves its partial of dot(dot_with, y) for dot_fold_kernel (no fence, no ticket: the blocks
+    //      are short, a memory round trip at the end of each would cost a quarter of the kernel) ----
+    if (halo_block && threadIdx.x == 0) {
+        unsigned int *ticket = reinterpret_cast<unsigned int *>(mine + 2);
+        const unsigned int old = atomicAdd(ticket, 1u);
+        if (old == (unsigned)(a.n_push_blocks + a.n_bnd_blocks) - 1) { *ticket = 0; mine[0] = e; }
     }
+    if (!DOT) return;
+    __shared__ T s_part[8];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) dot_acc = t_add<T>(dot_acc, __shfl_down_sync(0xffffffffu, dot_acc, off));
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = dot_acc;
@@ -220,44 +219,43 @@ __global__ void __launch_bounds__(256) dist_apply_kernel(const __grid_constant__
     if (threadIdx.x == 0) {
         T tot = s_part[0];
         for (int w = 1; w < 8; ++w) tot = t_add<T>(tot, s_part[w]);
-        reinterpret_cast<T *>(reinterpret_cast<char *>(a.dot_ws) + 64)[b] = tot;
-        __threadfence();
-        unsigned int *ticket = reinterpret_cast<unsigned int *>(a.dot_ws);
-        const unsigned int old = atomicAdd(ticket, 1u);
-        s_last = old == gridDim.x - 1;
-        if (s_last) { *ticket = 0; if (a.n_push_blocks + a.n_bnd_blocks > 0) mine[0] = ld_relaxed_sys(mine) + 1; }
+        reinterpret_cast<T *>(a.dot_ws)[b] = tot;
     }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // last block: fold the per-block partials in a fixed order (thread t takes blocks t, t+256, ...; then the shuffle tree)
-    const T *parts = reinterpret_cast<const T *>(reinterpret_cast<const char *>(a.dot_ws) + 64);
+}
+
+// Second (one-block) launch of a product + dot: folds the per-block partials in a fixed order (thread t takes partials
+// t, t + 1024, ...; then shuffle trees), combines the value across the GPUs through the reduction mailboxes (peer.cuh) and
+// stores it.  Every GPU ends with the same bits.
+template <class T>
+__global__ void __launch_bounds__(1024) dot_fold_kernel(const T *__restrict__ parts, unsigned int n, T *result, PeerArgs pa,
+                                                         unsigned long long *fault_host) {
+    __shared__ T s_part[32];
     T g = T(0);
-    for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) g = t_add<T>(g, __ldcg(parts + k));
+    for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) g = t_add<T>(g, parts[k]);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) g = t_add<T>(g, __shfl_down_sync(0xffffffffu, g, off));
-    __syncthreads();
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = g;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        T tot = s_part[0];
-        for (int w = 1; w < 8; ++w) tot = t_add<T>(tot, s_part[w]);
-        s_part[0] = tot;
+    if (threadIdx.x < 32) {
+        g = s_part[threadIdx.x];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) g = t_add<T>(g, __shfl_down_sync(0xffffffffu, g, off));
+        if (threadIdx.x == 0) s_part[0] = g;
     }
     __syncthreads();
-    if (a.pa.nranks > 1) {
+    if (pa.nranks > 1) {
         __shared__ unsigned long long px[VEXB_MAX_PEERS], py[VEXB_MAX_PEERS];
         unsigned long long bits = 0; { T t0 = s_part[0]; memcpy(&bits, &t0, sizeof(T)); }
-        const bool ok = peer_exchange(a.pa, bits, 0ull, px, py);
+        const bool ok = peer_exchange(pa, bits, 0ull, px, py);
         if (threadIdx.x == 0) {
             T tot; memcpy(&tot, &px[0], sizeof(T));
-            for (int r = 1; r < a.pa.nranks; ++r) { T v; memcpy(&v, &px[r], sizeof(T)); tot = t_add<T>(tot, v); }
+            for (int r = 1; r < pa.nranks; ++r) { T v; memcpy(&v, &px[r], sizeof(T)); tot = t_add<T>(tot, v); }
             s_part[0] = ok ? tot : nan_of<T>();
-            if (!ok && a.fault_host) *a.fault_host = ~0ull;
+            if (!ok && fault_host) *fault_host = ~0ull;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) a.dot_result[0] = s_part[0];
+    if (threadIdx.x == 0) result[0] = s_part[0];
 }
 
 } // namespace vexb
@@ -465,7 +463,7 @@ static int dist_apply_t(const vexb_dspmat *A, cudaStream_t st, const T *x, T *y,
     }
     const unsigned grid = (unsigned)(a.n_push_blocks + a.n_int_blocks + a.n_bnd_blocks);
     if (dot_with) {
-        const size_t need = 64 + (size_t)grid * 8;
+        const size_t need = (size_t)grid * 8;
         if (h->dot_ws_bytes < need) {                        // first use (outside any graph capture: callers warm up first)
             cudaFree(h->dot_ws); h->dot_ws = nullptr; h->dot_ws_bytes = 0;
             VEXB_CUDA(cudaMalloc(&h->dot_ws, need));
@@ -476,7 +474,11 @@ static int dist_apply_t(const vexb_dspmat *A, cudaStream_t st, const T *x, T *y,
     }
     if (fused_interior) {
         if (grid == 0) return VEXB_OK;
-        return dot_with ? launch_dist<T, true>(A, st, a, grid) : launch_dist<T, false>(A, st, a, grid);
+        if (!dot_with) return launch_dist<T, false>(A, st, a, grid);
+        VEXB_TRY((launch_dist<T, true>(A, st, a, grid)));
+        dot_fold_kernel<T><<<1, 1024, 0, st>>>((const T *)h->dot_ws, grid, dot_result, a.pa, h->fault_host);
+        VEXB_LAUNCHED();
+        return VEXB_OK;
     }
     // interior as its own kernel (CSR / row patterns / empty), halo + boundary rows beside it
     VEXB_CUDA(cudaEventRecord(A->ev_x, st));

@@ -355,9 +355,9 @@ extern "C" int vexb_dspmat_apply(int nlocal, vexb_comm *const *comms, vexb_dspma
     return VEXB_OK;
 }
 
-// y (=|+=) alpha*A*x and, in the same launch, d_result = sum over ALL parts of dot_with . y_new (combined across the GPUs
-// of `peers` inside the kernel, every GPU ends with the same bits).  This is q = A p; (p, q) of a CG iteration as one
-// kernel per GPU (the reference fuses the product into a consumer kernel on one device: sparse/product.hpp:45-130,
+// y (=|+=) alpha*A*x with the partials of dot_with . y_new computed in the product kernel's epilogue, then a one-block
+// fold that also combines across the GPUs of `peers` (every GPU ends with the same bits).  This is q = A p; (p, q) of a CG
+// iteration without re-reading p and q (the reference fuses the product into a consumer kernel on one device: sparse/product.hpp:45-130,
 // spmat/inline_spmv.hpp:68-76; its multi-device SpMat needs a separate reduction).  Needs the peer-memory halo on every
 // part (or a single part) and a hybrid-ELL interior strip: otherwise VEXB_ERR_UNSUPPORTED and the caller composes it.
 extern "C" int vexb_dspmat_apply_dot(int nlocal, vexb_dspmat *const *parts, void *const *streams, const void *const *x,
@@ -376,5 +376,26 @@ extern "C" int vexb_dspmat_apply_dot(int nlocal, vexb_dspmat *const *parts, void
     for (int k = 0; k < nlocal; ++k)
         VEXB_TRY(dist_apply(parts[k], (cudaStream_t)(streams ? streams[k] : nullptr), x[k], y[k], alpha, append, dot_with[k], d_result[k],
                             parts[k]->nparts > 1 ? peers[k] : nullptr));
+    return VEXB_OK;
+}
+
+// SpMat::apply for nrhs vectors at once (vex::SpMat * vex::multivector): x[k * nrhs + r], y[k * nrhs + r] are part k's slices
+// of component r.  Parts without a halo multiply all components in one pass over the matrix (vexb_spmv_multi); with a halo
+// the components go through vexb_dspmat_apply one after the other, as the reference does (operations.hpp:876-880).
+extern "C" int vexb_dspmat_apply_multi(int nlocal, vexb_comm *const *comms, vexb_dspmat *const *parts, void *const *streams,
+                                       int nrhs, const void *const *x, void *const *y, double alpha, int append) {
+    VEXB_CHECK(nlocal >= 1 && nrhs >= 1 && parts && x && y, "bad arguments");
+    bool halo = false;
+    for (int k = 0; k < nlocal; ++k) { VEXB_CHECK(parts[k], "part %d is NULL", k); halo = halo || parts[k]->n_send || parts[k]->n_ghost; }
+    if (!halo) {
+        for (int k = 0; k < nlocal; ++k)
+            VEXB_TRY(vexb_spmv_multi(parts[k]->dev, streams ? streams[k] : nullptr, parts[k]->loc, nrhs, x + (size_t)k * nrhs, y + (size_t)k * nrhs, alpha, append));
+        return VEXB_OK;
+    }
+    std::vector<const void *> xs(nlocal); std::vector<void *> ys(nlocal);
+    for (int r = 0; r < nrhs; ++r) {
+        for (int k = 0; k < nlocal; ++k) { xs[k] = x[(size_t)k * nrhs + r]; ys[k] = y[(size_t)k * nrhs + r]; }
+        VEXB_TRY(vexb_dspmat_apply(nlocal, comms, parts, streams, xs.data(), ys.data(), alpha, append));
+    }
     return VEXB_OK;
 }

@@ -151,8 +151,11 @@ static int fold_compound(const vexb_expr &e, const void *lhs, int lhs_dtype, int
                                 VEXB_OP_BAND, VEXB_OP_BOR, VEXB_OP_BXOR, VEXB_OP_SHL, VEXB_OP_SHR};
     VEXB_CHECK(aop > VEXB_SET && aop <= VEXB_RSH, "bad assign op %d", aop);
     const int R = host_result_type(e);
-    const int C = common_dtype(lhs_dtype, R);
-    if (aop >= VEXB_MOD && dtype_is_float(C))
+    // shifts keep the (promoted) type of the LEFT operand, only the count comes from the right: `a >>= b` on a signed a
+    // is an arithmetic shift whatever the type of b (C/C++ [expr.shift]; the reference emits `lhs[i] >>= rhs`)
+    const bool shift = aop == VEXB_LSH || aop == VEXB_RSH;
+    const int C = shift ? lhs_dtype : common_dtype(lhs_dtype, R);
+    if (aop >= VEXB_MOD && (dtype_is_float(C) || (shift && dtype_is_float(R))))
         VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "compound assignment %d is not defined for floating operands", aop);
     VEXB_CHECK(e.n_terms < VEXB_MAX_TERMS, "too many terminals for compound assignment");
     VEXB_CHECK(e.n_code + 4 <= VEXB_MAX_CODE, "program too long for compound assignment");

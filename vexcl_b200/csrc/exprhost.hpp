@@ -130,15 +130,30 @@ inline int normalize_expr(const vexb_expr *in, vexb_expr *out, bool need_ptrs = 
         } else if (ins.op == VEXB_OP_CVT) {
             VEXB_CHECK(ins.arg <= VEXB_U64, "instr %d: bad CVT source type", pc);
             // 2. fold a conversion applied directly to a scalar terminal.
-            vexb_instr &prev = out->code[out->n_code - 1];
-            if (out->n_code > 0 && prev.op == VEXB_OP_TERM && out->term[prev.arg].kind == VEXB_TERM_SCALAR) {
-                vexb_term t = out->term[prev.arg];
-                convert_scalar_term(t, ins.type);
-                VEXB_CHECK(out->n_terms < VEXB_MAX_TERMS, "too many terminals");
-                const int slot = out->n_terms++;
-                out->term[slot] = t;
-                prev.arg = (uint16_t)slot; prev.type = ins.type;
-                continue;
+            if (out->n_code > 0) {
+                vexb_instr &prev = out->code[out->n_code - 1];
+                if (prev.op == VEXB_OP_TERM && out->term[prev.arg].kind == VEXB_TERM_SCALAR) {
+                    vexb_term t = out->term[prev.arg];
+                    convert_scalar_term(t, ins.type);
+                    int refs = 0;                                        // other pushes of the same scalar slot keep its old type
+                    for (int q = 0; q < out->n_code; ++q) if (out->code[q].op == VEXB_OP_TERM && out->code[q].arg == prev.arg) ++refs;
+                    bool shared = refs > 1;
+                    for (int q = 0; !shared && q < VEXB_MAX_TERMS; ++q) if (remap[q] == (int)prev.arg) {
+                        // a later instruction of the input may push this input slot again: look ahead
+                        for (int r = pc + 1; r < in->n_code; ++r) if (in->code[r].op == VEXB_OP_TERM && in->code[r].arg == q) shared = true;
+                    }
+                    if (!shared) {
+                        out->term[prev.arg] = t;                          // referenced once: fold in place, no new slot
+                        for (int q = 0; q < VEXB_MAX_TERMS; ++q) if (remap[q] == (int)prev.arg) remap[q] = -1;
+                    } else {
+                        VEXB_CHECK(out->n_terms < VEXB_MAX_TERMS, "too many terminals");
+                        const int slot = out->n_terms++;
+                        out->term[slot] = t;
+                        prev.arg = (uint16_t)slot;
+                    }
+                    prev.type = ins.type;
+                    continue;
+                }
             }
             if (ins.arg == ins.type) continue; // no-op conversion
         } else if (ins.op >= VEXB_OP_BAND && ins.op <= VEXB_OP_SHR) {

@@ -311,6 +311,59 @@ __global__ void __launch_bounds__(256) reduce_interp_kernel(const __grid_constan
     block_finish<OP, T>(f, ws, result, pa);
 }
 
+// ---- several reductions of ONE expression in one pass: vex::CombineReductors<R...> (reductor.hpp:132-280) ------------
+// The expression is evaluated once per element and fed to up to VEXB_MAX_COMBINED folds; every fold then finishes like a
+// single reduction (its own partials and ticket in its own slice of the workspace, its own combine across the GPUs).
+template <class T>
+struct RtFold {
+    T x, y;
+    __device__ __forceinline__ void init(int op) {
+        x = (op == VEXB_MAX) ? Lim<T>::lowest() : (op == VEXB_MIN) ? Lim<T>::highest() : T(0); y = T(0);
+    }
+    __device__ __forceinline__ void take(int op, T v) {
+        if (op == VEXB_SUM) x = red_add<T>(x, v);
+        else if (op == VEXB_SUM_KAHAN) { const T yy = red_sub<T>(v, y); const T t = red_add<T>(x, yy); y = red_sub<T>(red_sub<T>(t, x), yy); x = t; }
+        else if (op == VEXB_MAX) x = x > v ? x : v;
+        else x = x < v ? x : v;
+    }
+    __device__ __forceinline__ void merge(int op, const RtFold &o) {
+        if (op == VEXB_SUM || op == VEXB_SUM_KAHAN) x = red_add<T>(x, o.x);
+        else if (op == VEXB_MAX) x = x > o.x ? x : o.x;
+        else x = x < o.x ? x : o.x;
+    }
+};
+
+struct MultiOps { int n; int op[VEXB_MAX_COMBINED]; };
+
+template <class T, int U>
+__global__ void __launch_bounds__(256) reduce_multi_kernel(const __grid_constant__ vexb_expr e, int dtype, size_t n, size_t index_offset,
+                                                            MultiOps ops, void *ws, size_t ws_stride, T *result, PeerArgs pa) {
+    const int rt = program_result_type(e);
+    RtFold<T> acc[VEXB_MAX_COMBINED];
+    for (int k = 0; k < ops.n; ++k) acc[k].init(ops.op[k]);
+    const size_t chunk = (size_t)blockDim.x * U;
+    for (size_t base = (size_t)blockIdx.x * chunk; base < n; base += (size_t)gridDim.x * chunk) {
+        size_t idx[U]; bool active[U]; V out[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { idx[u] = base + (size_t)u * blockDim.x + threadIdx.x; active[u] = idx[u] < n; }
+        eval_expr<U>(e, idx, active, index_offset, out);
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (active[u]) {
+            const T v = v_as<T>(convert(out[u], rt, dtype));
+            for (int k = 0; k < ops.n; ++k) acc[k].take(ops.op[k], v);
+        }
+    }
+    for (int k = 0; k < ops.n; ++k) {
+        void *wk = reinterpret_cast<char *>(ws) + (size_t)k * ws_stride;
+        switch (ops.op[k]) {          // uniform across the block: the barriers inside block_finish are safe
+            case VEXB_MAX: { Fold<VEXB_MAX, T> f; f.x = acc[k].x; f.y = T(0); block_finish<VEXB_MAX, T>(f, wk, result + k, pa); break; }
+            case VEXB_MIN: { Fold<VEXB_MIN, T> f; f.x = acc[k].x; f.y = T(0); block_finish<VEXB_MIN, T>(f, wk, result + k, pa); break; }
+            default:       { Fold<VEXB_SUM, T> f; f.x = acc[k].x; f.y = T(0); block_finish<VEXB_SUM, T>(f, wk, result + k, pa); break; }
+        }
+        __syncthreads();
+    }
+}
+
 template <int OP, class T>
 __global__ void identity_kernel(T *result) {
     Fold<OP, T> f; f.init();
@@ -500,6 +553,56 @@ extern "C" int vexb_cg_update_xp(int dev, void *stream, int dtype, size_t n, voi
                                 (const double *)d_rho, (const double *)d_pq, (const double *)d_rho_new);
     else cg_update_xp_kernel<float, 1><<<(unsigned)want, 256, 0, st>>>(n, (float *)x, (float *)p, (const float *)r,
                                 (const float *)d_rho, (const float *)d_pq, (const float *)d_rho_new);
+    VEXB_LAUNCHED();
+    return VEXB_OK;
+}
+
+template <class T>
+static void launch_rmulti(int blocks, cudaStream_t st, const vexb_expr &e, int dtype, size_t n, size_t off, const vexb::MultiOps &ops,
+                          void *ws, size_t stride, void *res, const PeerArgs &pa) {
+    vexb::reduce_multi_kernel<T, 4><<<blocks, 256, 0, st>>>(e, dtype, n, off, ops, ws, stride, (T *)res, pa);
+}
+
+extern "C" int vexb_reduce_multi(int dev, void *stream, const vexb_expr *expr, int dtype, size_t n, size_t index_offset,
+                                 int nops, const int *ops, void *d_result, void *d_workspace, vexb_peer *peer) {
+    VEXB_CHECK(nops >= 1 && nops <= VEXB_MAX_COMBINED && ops, "between 1 and %d reductions can be combined", VEXB_MAX_COMBINED);
+    VEXB_CHECK(dtype >= VEXB_F64 && dtype <= VEXB_U64, "bad dtype %d", dtype);
+    VEXB_CHECK(d_result && d_workspace, "d_result / d_workspace is NULL");
+    MultiOps mo; mo.n = nops;
+    for (int k = 0; k < nops; ++k) {
+        VEXB_CHECK(ops[k] >= VEXB_SUM && ops[k] <= VEXB_MIN, "reduction %d: only SUM, SUM_Kahan, MAX and MIN combine", k);
+        mo.op[k] = (ops[k] == VEXB_SUM_KAHAN && !dtype_is_float(dtype)) ? VEXB_SUM : ops[k];
+    }
+    PeerArgs pa; memset(&pa, 0, sizeof(pa));
+    if (peer && peer->nranks > 1) { VEXB_CHECK(peer->dev == dev, "peer group lives on device %d, not %d", peer->dev, dev); pa = peer->args(); }
+    vexb_expr e;
+    VEXB_TRY(normalize_expr(expr, &e, n != 0));
+    if (expr_has_call(e)) VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "reductions of expressions that call user functions are evaluated into a temporary first");
+    const size_t es = dtype_size(dtype);
+    if (n == 0) {
+        for (int k = 0; k < nops; ++k) {
+            VEXB_TRY(vexb_reduce_identity(dev, stream, dtype, mo.op[k], (char *)d_result + (size_t)k * es));
+            if (pa.nranks > 1) VEXB_TRY(vexb_peer_allreduce(peer, stream, (char *)d_result + (size_t)k * es, dtype, mo.op[k]));
+        }
+        return VEXB_OK;
+    }
+    DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
+    size_t stride = 0;
+    VEXB_TRY(vexb_reduce_workspace_bytes(dev, &stride));
+    long bps = param("reduce.blocks_per_sm", 8);
+    if (bps < 1) bps = 1; if (bps > kMaxBlocksPerSm) bps = kMaxBlocksPerSm;
+    const size_t cap = (size_t)sm_count(dev) * (size_t)bps;
+    size_t want = (n + 1023) / 1024;
+    const int blocks = (int)(want < cap ? want : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case VEXB_F64: launch_rmulti<double>(blocks, st, e, dtype, n, index_offset, mo, d_workspace, stride, d_result, pa); break;
+        case VEXB_F32: launch_rmulti<float>(blocks, st, e, dtype, n, index_offset, mo, d_workspace, stride, d_result, pa); break;
+        case VEXB_I32: launch_rmulti<int>(blocks, st, e, dtype, n, index_offset, mo, d_workspace, stride, d_result, pa); break;
+        case VEXB_U32: launch_rmulti<unsigned>(blocks, st, e, dtype, n, index_offset, mo, d_workspace, stride, d_result, pa); break;
+        case VEXB_I64: launch_rmulti<long long>(blocks, st, e, dtype, n, index_offset, mo, d_workspace, stride, d_result, pa); break;
+        default:       launch_rmulti<unsigned long long>(blocks, st, e, dtype, n, index_offset, mo, d_workspace, stride, d_result, pa); break;
+    }
     VEXB_LAUNCHED();
     return VEXB_OK;
 }

@@ -376,6 +376,58 @@ __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w
     store_y<T>(y, row_ids ? (size_t)row_ids[i] : i, sum, alpha, append);
 }
 
+// ---- several right-hand sides at once: SpMat * multivector (vexcl/multivector.hpp, operations.hpp:861-881) ------------
+// The reference multiplies component by component and streams the matrix K times.  Here a row's columns and values are
+// loaded once and used for K gathers / K sums: for configs[2] with K = 4 that is 50 + 4*16 = 114 bytes per row instead
+// of 4 * 66.  Per component the products are added in the same order as in hell_kernel (same bits).
+template <int K> struct MultiPtr { const void *x[K]; void *y[K]; };
+
+template <class T, int W, class C, int K>
+__global__ void __launch_bounds__(256) hell_multi_kernel(size_t n, size_t pitch, int w_dyn, const C *__restrict__ ell_col, int shift,
+                                                          const T *__restrict__ ell_val, const int *__restrict__ tail_ptr,
+                                                          const int *__restrict__ tail_col, const T *__restrict__ tail_val,
+                                                          MultiPtr<K> mp, T alpha, int append, const int *__restrict__ row_ids, size_t y_offset) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
+    T sum[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) sum[k] = T(0);
+    if (W > 0) {
+        int c[W > 0 ? W : 1]; T v[W > 0 ? W : 1];
+#pragma unroll
+        for (int j = 0; j < W; ++j) { c[j] = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const T *x = static_cast<const T *>(mp.x[k]);
+            T xv[W > 0 ? W : 1];
+#pragma unroll
+            for (int j = 0; j < W; ++j) xv[j] = (c[j] != -1) ? ldg_keep(x + c[j], keep) : T(0);
+#pragma unroll
+            for (int j = 0; j < W; ++j) if (c[j] != -1) sum[k] = t_add<T>(sum[k], t_mul<T>(v[j], xv[j]));
+        }
+    } else {
+        for (int j = 0; j < w_dyn; ++j) {
+            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift);
+            if (c != -1) {
+                const T v = ldg_stream(ell_val + i + (size_t)j * pitch, stream);
+#pragma unroll
+                for (int k = 0; k < K; ++k) sum[k] = t_add<T>(sum[k], t_mul<T>(v, ldg_keep(static_cast<const T *>(mp.x[k]) + c, keep)));
+            }
+        }
+    }
+    if (tail_ptr) {
+        for (int j = tail_ptr[i], e = tail_ptr[i + 1]; j < e; ++j) {
+            const T v = tail_val[j]; const int c = tail_col[j];
+#pragma unroll
+            for (int k = 0; k < K; ++k) sum[k] = t_add<T>(sum[k], t_mul<T>(v, __ldg(static_cast<const T *>(mp.x[k]) + c)));
+        }
+    }
+    const size_t r = row_ids ? (size_t)row_ids[i] : i + y_offset;
+#pragma unroll
+    for (int k = 0; k < K; ++k) store_y<T>(static_cast<T *>(mp.y[k]), r, sum[k], alpha, append);
+}
+
 // spmv.kernel = 3: one thread per row straight from the CSR arrays ("CSR-scalar").  Neighbouring lanes read
 // neighbouring rows, i.e. addresses a row length apart: not coalesced per instruction, but every 32-byte sector a warp
 // touches is consumed completely by it over the row loop, so with L1 allocation (plain loads, no streaming hint) DRAM
@@ -415,17 +467,24 @@ constexpr int kWarpTileNnz = 256;
 constexpr int kWarpTileRows = 256;
 constexpr int kWarpPer = kWarpTileNnz / 32;
 
+// Row sums of one warp tile from the products parked in shared memory.  G lanes share a row (G = 1: one lane per row,
+// storage order); pass p covers rows p*(32/G) .. ; the row pointers of the first two passes arrive preloaded (pa/pb), the
+// rest are fetched here.
 template <class T, int G>
 __device__ __forceinline__ void warp_rows(const T *prod, const int *__restrict__ rowptr, int r0, int nr, int j0, int lane,
-                                          T *y, T alpha, int append, const int *__restrict__ row_ids) {
-    // groups of G lanes per row; G == 1: one lane per row, storage order
+                                          const int (&pa)[2], const int (&pb)[2], T *y, T alpha, int append,
+                                          const int *__restrict__ row_ids) {
     constexpr int RPW = 32 / G;                       // rows per warp pass
     const int sub = lane % G, grp = lane / G;
-    for (int rb = 0; rb < nr; rb += RPW) {
+    int pass = 0;
+    for (int rb = 0; rb < nr; rb += RPW, ++pass) {
         const int r = rb + grp;
         T s = T(0);
         if (r < nr) {
-            const int a = __ldg(rowptr + r0 + r) - j0, b = __ldg(rowptr + r0 + r + 1) - j0;
+            int a, b;
+            if (pass == 0) { a = pa[0]; b = pb[0]; } else if (pass == 1) { a = pa[1]; b = pb[1]; }
+            else { a = __ldg(rowptr + r0 + r); b = __ldg(rowptr + r0 + r + 1); }
+            a -= j0; b -= j0;
             for (int j = a + sub; j < b; j += G) s = t_add<T>(s, prod[j]);
         }
         if (G > 1) {
@@ -435,6 +494,9 @@ __device__ __forceinline__ void warp_rows(const T *prod, const int *__restrict__
         if (r < nr && sub == 0) store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, s, alpha, append);
     }
 }
+
+// lanes per row for a tile of cnt nonzeros in nr rows
+__device__ __forceinline__ int warp_tile_group(int cnt, int nr) { return cnt <= 6 * nr ? 1 : cnt <= 24 * nr ? 4 : cnt <= 64 * nr ? 8 : 32; }
 
 template <class T>
 __global__ void __launch_bounds__(256, 4) csr_warp_kernel(const int2 *__restrict__ tile, int n_tiles, const int *__restrict__ rowptr,
@@ -448,12 +510,35 @@ __global__ void __launch_bounds__(256, 4) csr_warp_kernel(const int2 *__restrict
     int t = blockIdx.x * 8 + warp;
     if (t >= n_tiles) return;
     const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
-    int2 d0 = __ldg(tile + t), d1 = __ldg(tile + t + 1);
+
+    // Software pipeline over the tiles t, t + W, t + 2W, ... of this warp.  While the row sums of tile i are computed from
+    // shared memory, the col/val/row-pointer loads of tile i+1 are already in flight (their registers are free again once
+    // the products of tile i are parked), and the descriptor of tile i+2 is on its way.
+    int2 d0 = __ldg(tile + t), d1 = __ldg(tile + t + 1);                 // current
+    int2 n0 = d0, n1 = d1;                                               // next
+    { const int tn = t + total_warps; if (tn < n_tiles) { n0 = __ldg(tile + tn); n1 = __ldg(tile + tn + 1); } }
+    int c[kWarpPer]; T v[kWarpPer]; int pa[2], pb[2];
+    auto issue = [&](const int2 &e0, const int2 &e1) {
+        const int r0 = e0.x, nr = e1.x - e0.x, j0 = e0.y, cnt = e1.y - e0.y;
+        if (cnt > kWarpTileNnz || nr <= 0) return;
+#pragma unroll
+        for (int k = 0; k < kWarpPer; ++k) {
+            const int j = lane + 32 * k;
+            if (j < cnt) { c[k] = ldg_stream(col + j0 + j, stream); v[k] = ldg_stream(val + j0 + j, stream); }
+        }
+        const int G = warp_tile_group(cnt, nr), rpw = 32 / G, grp = lane / G;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int r = p * rpw + grp;
+            if (r < nr) { pa[p] = __ldg(rowptr + r0 + r); pb[p] = __ldg(rowptr + r0 + r + 1); }
+        }
+    };
+    issue(d0, d1);
     while (true) {
-        const int tn = t + total_warps;
-        int2 n0 = d0, n1 = d1;
-        if (tn < n_tiles) { n0 = __ldg(tile + tn); n1 = __ldg(tile + tn + 1); }        // next descriptor: in flight during this tile
+        const int tn = t + total_warps, tnn = tn + total_warps;
         const int r0 = d0.x, nr = d1.x - d0.x, j0 = d0.y, cnt = d1.y - d0.y;
+        int2 m0 = n0, m1 = n1;                                           // descriptor after next
+        if (tnn < n_tiles) { m0 = __ldg(tile + tnn); m1 = __ldg(tile + tnn + 1); }
         if (cnt > kWarpTileNnz) {
             // one long row: the warp strides over it
             T s = T(0);
@@ -461,13 +546,8 @@ __global__ void __launch_bounds__(256, 4) csr_warp_kernel(const int2 *__restrict
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s = t_add<T>(s, __shfl_down_sync(0xffffffffu, s, off));
             if (lane == 0) store_y<T>(y, row_ids ? (size_t)row_ids[r0] : (size_t)r0, s, alpha, append);
+            if (tn < n_tiles) issue(n0, n1);
         } else if (nr > 0) {
-            int c[kWarpPer]; T v[kWarpPer];
-#pragma unroll
-            for (int k = 0; k < kWarpPer; ++k) {
-                const int j = lane + 32 * k;
-                if (j < cnt) { c[k] = ldg_stream(col + j0 + j, stream); v[k] = ldg_stream(val + j0 + j, stream); }
-            }
 #pragma unroll
             for (int k = 0; k < kWarpPer; ++k) {
                 const int j = lane + 32 * k;
@@ -478,15 +558,19 @@ __global__ void __launch_bounds__(256, 4) csr_warp_kernel(const int2 *__restrict
                 const int j = lane + 32 * k;
                 if (j < cnt) prod[j] = v[k];
             }
+            const int qa[2] = {pa[0], pa[1]}, qb[2] = {pb[0], pb[1]};
             __syncwarp();
-            if (cnt <= 6 * nr)        warp_rows<T, 1>(prod, rowptr, r0, nr, j0, lane, y, alpha, append, row_ids);
-            else if (cnt <= 24 * nr)  warp_rows<T, 4>(prod, rowptr, r0, nr, j0, lane, y, alpha, append, row_ids);
-            else if (cnt <= 64 * nr)  warp_rows<T, 8>(prod, rowptr, r0, nr, j0, lane, y, alpha, append, row_ids);
-            else                      warp_rows<T, 32>(prod, rowptr, r0, nr, j0, lane, y, alpha, append, row_ids);
+            if (tn < n_tiles) issue(n0, n1);                             // next tile's loads fly during the row sums below
+            switch (warp_tile_group(cnt, nr)) {
+                case 1:  warp_rows<T, 1>(prod, rowptr, r0, nr, j0, lane, qa, qb, y, alpha, append, row_ids); break;
+                case 4:  warp_rows<T, 4>(prod, rowptr, r0, nr, j0, lane, qa, qb, y, alpha, append, row_ids); break;
+                case 8:  warp_rows<T, 8>(prod, rowptr, r0, nr, j0, lane, qa, qb, y, alpha, append, row_ids); break;
+                default: warp_rows<T, 32>(prod, rowptr, r0, nr, j0, lane, qa, qb, y, alpha, append, row_ids); break;
+            }
             __syncwarp();
-        }
+        } else if (tn < n_tiles) issue(n0, n1);
         if (tn >= n_tiles) break;
-        t = tn; d0 = n0; d1 = n1;
+        t = tn; d0 = n0; d1 = n1; n0 = m0; n1 = m1;
     }
 }
 
@@ -574,11 +658,14 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
         std::vector<int> idx, prow, pcol; std::vector<T> pval;
         const size_t limit = (size_t)std::max(1l, std::min(param("spmv.max_patterns", 256), 65536l));
         if (plain && n > 0 && A->nnz > 0 && find_row_patterns<T>(n, rowptr, col, val, limit, idx, prow, pcol, pval)) {
-            A->fmt = VEXB_FMT_PATTERNS;
-            A->n_patterns = prow.size() - 1;
-            VEXB_TRY(ccsr_create_ex(A->dev, n, A->ncols, A->n_patterns, idx.data(), 4, prow.data(), 4, pcol.data(), 4, pval.data(),
-                                    A->val_dtype, &A->patterns));
-            return VEXB_OK;
+            // a strip the CCSR kernel cannot take (e.g. too many entries in the unique-row table) is simply not compressed
+            if (ccsr_create_ex(A->dev, n, A->ncols, prow.size() - 1, idx.data(), 4, prow.data(), 4, pcol.data(), 4, pval.data(),
+                               A->val_dtype, &A->patterns) == VEXB_OK) {
+                A->fmt = VEXB_FMT_PATTERNS;
+                A->n_patterns = prow.size() - 1;
+                return VEXB_OK;
+            }
+            A->patterns = nullptr;
         }
         fmt = VEXB_FMT_AUTO;
     }
@@ -778,6 +865,26 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
     return VEXB_OK;
 }
 
+template <class T, int K>
+static int spmv_multi_launch(const vexb_spmat *A, cudaStream_t st, const void *const *x, void *const *y, T alpha, int append) {
+    const size_t n = A->nrows_stored;
+    MultiPtr<K> mp;
+    for (int k = 0; k < K; ++k) { mp.x[k] = x[k]; mp.y[k] = y[k]; }
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+#define HM(W) do { \
+        if (A->ell_col16) hell_multi_kernel<T, W, short, K><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col16, A->ell_shift, \
+              (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, mp, alpha, append, A->row_ids, A->y_offset); \
+        else hell_multi_kernel<T, W, int, K><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col, 0, \
+              (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, mp, alpha, append, A->row_ids, A->y_offset); } while (0)
+    switch (A->ell_width) {
+        case 3: HM(3); break; case 5: HM(5); break; case 7: HM(7); break;
+        default: HM(0); break;
+    }
+#undef HM
+    VEXB_LAUNCHED();
+    return VEXB_OK;
+}
+
 } // namespace vexb
 
 int vexb::spmat_from_csr(int dev, size_t nrows, size_t ncols, std::vector<int> &rowptr, std::vector<int> &col,
@@ -922,4 +1029,31 @@ extern "C" int vexb_spmv(int dev, void *stream, const vexb_spmat *A, const void 
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     if (A->val_dtype == VEXB_F64) return spmv_launch<double>(A, (cudaStream_t)stream, (const double *)x, (double *)y, alpha, append);
     return spmv_launch<float>(A, (cudaStream_t)stream, (const float *)x, (float *)y, (float)alpha, append);
+}
+
+// y_k (=|+=) alpha * A x_k for k < nrhs, the matrix streamed once per group of up to 4 right-hand sides (hybrid-ELL
+// strips); other formats, and single vectors, go through vexb_spmv one by one.  vex::SpMat * vex::multivector.
+extern "C" int vexb_spmv_multi(int dev, void *stream, const vexb_spmat *A, int nrhs, const void *const *x, void *const *y,
+                               double alpha, int append) {
+    VEXB_CHECK(A && nrhs >= 1 && x && y, "bad arguments");
+    VEXB_CHECK(dev == A->dev, "matrix lives on device %d, not %d", A->dev, dev);
+    for (int k = 0; k < nrhs; ++k) VEXB_CHECK((A->nrows == 0 || y[k]) && (A->nnz == 0 || x[k]), "vector %d is NULL", k);
+    const bool fused = A->fmt == VEXB_FMT_HELL && A->nnz > 0 && A->nrows_stored > 0 && nrhs > 1 && !param("spmv.no_multi", 0);
+    if (!fused) {
+        for (int k = 0; k < nrhs; ++k) VEXB_TRY(vexb_spmv(dev, stream, A, x[k], y[k], alpha, append));
+        return VEXB_OK;
+    }
+    DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int k0 = 0; k0 < nrhs;) {
+        const int rest = nrhs - k0;
+        const int K = rest >= 4 ? 4 : rest;                  // groups of 4, then 3 / 2 / 1
+        if (K == 1) { VEXB_TRY(vexb_spmv(dev, stream, A, x[k0], y[k0], alpha, append)); break; }
+#define GO(T, KK) VEXB_TRY((spmv_multi_launch<T, KK>(A, st, x + k0, y + k0, (T)alpha, append)))
+        if (A->val_dtype == VEXB_F64) { if (K == 4) GO(double, 4); else if (K == 3) GO(double, 3); else GO(double, 2); }
+        else { if (K == 4) GO(float, 4); else if (K == 3) GO(float, 3); else GO(float, 2); }
+#undef GO
+        k0 += K;
+    }
+    return VEXB_OK;
 }

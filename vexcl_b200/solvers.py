@@ -83,10 +83,11 @@ class CGDevice:
 
 
 class CGFused:
-    """The same iteration in three launches per GPU (BASELINE configs[4], "fused CG step"):
+    """The same iteration in four launches per GPU (BASELINE configs[4], "fused CG step"):
 
-        q = A p  and  (p, q)                                   one kernel: SpMat.apply_dot (halo pushed over NVLink peer memory,
-                                                               dot combined across GPUs inside the kernel)
+        q = A p  and  (p, q)                                   SpMat.apply_dot: the product kernel (halo pushed over NVLink peer
+                                                               memory) leaves per-block partials of (p, q); a one-block kernel
+                                                               folds them and combines across the GPUs
         alpha = rho/(p,q); r -= alpha q; rho' = (r, r)         one sweep (vexb_cg_update_r), combine in the kernel
         beta = rho'/rho; x += alpha p; p = r + beta p          one sweep (vexb_cg_update_xp)
 
