@@ -581,6 +581,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         extra["reduce_all"] = bench_reduce_bits(ctx, vx, L, rank, world, dist)
     except vx.VexbError as e:
         extra["reduce_all"] = {"error": str(e)}
+    if world == 1:
+        try:
+            extra["multi_rhs"] = bench_multi_rhs(ctx, vx, A, N, step_bytes, args, barrier, peak)
+        except vx.VexbError as e:
+            extra["multi_rhs"] = {"error": str(e)}
+    if world == 1:
+        try:
+            extra["fused_product"] = bench_fused_product(ctx, vx, A, N, step_bytes, args, barrier, peak)
+        except vx.VexbError as e:
+            extra["fused_product"] = {"error": str(e)}
     if A_alt is not None:
         extra["csr_kernels"] = bench_csr_kernels(ctx, vx, gen, A_alt, x, y, step_bytes, args, barrier, peak)
         extra["csr_stream_kernel"] = extra["csr_kernels"]["configs[2] forced to CSR"]["default"]
@@ -678,6 +688,41 @@ def bench_csr_kernels(ctx, vx, gen, A_csr, x, y, nbytes, args, barrier, peak):
     out["note"] = ("default = the strip's own choice (thread per row for short even rows, warp tiles otherwise); "
                    "tma_cta_tiles = the round-1 one-shot TMA kernel")
     return out
+
+
+def bench_multi_rhs(ctx, vx, A, N, nbytes_one, args, barrier, peak):
+    """vex::SpMat * vex::multivector<double,4> on configs[2]: the matrix is streamed once for the four right-hand sides."""
+    steps = max(args.steps, 20)
+    xs = [vx.vector(ctx, N) for _ in range(4)]
+    ys = [vx.vector(ctx, N) for _ in range(4)]
+    for r, v in enumerate(xs):
+        v.assign(vx.ElementIndex() * (1.0 / N) + 0.25 * r)
+    one = time_loop(ctx, lambda: A.apply(xs[0], ys[0], 1.0, False), steps, 3, barrier) / steps
+    four = time_loop(ctx, lambda: A.apply_multi(xs, ys, 1.0, False), steps, 3, barrier) / steps
+    vx.set_param("spmv.no_multi", 1)
+    sep = time_loop(ctx, lambda: A.apply_multi(xs, ys, 1.0, False), steps, 3, barrier) / steps
+    vx.set_param("spmv.no_multi", 0)
+    return {"ms_one_vector": one, "ms_four_vectors_one_pass": four, "ms_four_separate_products": sep, "ratio_to_one_vector": four / one,
+            "gbs_as_four_products": 4 * nbytes_one / (four * 1e-3) / 1e9,
+            "note": "per row: matrix entries once + 4 x (x + y); four separate products is what the reference does (operations.hpp:876-880)"}
+
+
+def bench_fused_product(ctx, vx, A, N, nbytes, args, barrier, peak):
+    """`y = x + A*x` as one generated kernel (the product inlined into the consumer, sparse/product.hpp:45-130) against the
+    plain product and against the unfused composition (vector part, then y += A*x) on configs[2]."""
+    steps = max(args.steps, 20)
+    x, y = vx.vector(ctx, N), vx.vector(ctx, N)
+    x.assign(vx.ElementIndex() * (1.0 / N) + 0.5)
+    plain = time_loop(ctx, lambda: A.apply(x, y, 1.0, False), steps, 3, barrier) / steps
+    fused = time_loop(ctx, lambda: y.assign(x + A * x), steps, 3, barrier) / steps
+    ctx.fuse_products = False
+    try:
+        unfused = time_loop(ctx, lambda: y.assign(x + A * x), steps, 3, barrier) / steps
+    finally:
+        ctx.fuse_products = True
+    return {"ms_y=A*x": plain, "ms_y=x+A*x_one_kernel": fused, "ms_y=x+A*x_two_kernels": unfused, "ratio_fused_to_plain": fused / plain,
+            "gbs_fused": (nbytes + 8 * N) / (fused * 1e-3) / 1e9,
+            "note": "fused: NVRTC kernel with the hybrid-ELL row loop generated into it (VEXB_TERM_SPMV); x[i] is one more 8-byte read per row"}
 
 
 def bench_cg(ctx, vx, rank, world, args, barrier, max_over_ranks, sum_over_ranks, peak):
@@ -855,6 +900,27 @@ def bench_vectors(ctx, vx, args, peak):
         ms = time_loop(ctx, fn, steps, 3, ctx.finish)
         gbs = bpe * n * steps / (ms * 1e-3) / 1e9
         out[name] = {"gbs": gbs, "frac_of_peak": gbs / peak, "ms": ms / steps, "bytes_per_elem": bpe, "n": n}
+    # an expression without a hand-written sweep: interpreter, then the NVRTC kernel built in the background at first use
+    import ctypes as C
+    gen_expr = lambda: a.assign((b - c) * (b + c) / d + b * 0.5 + c * d)
+    vx.set_param("eval.jit", 0)
+    ms_i = time_loop(ctx, gen_expr, steps, 3, ctx.finish) / steps
+    vx.set_param("eval.jit", 2)
+    t0 = time.perf_counter()
+    gen_expr(); ctx.finish()                               # first use in default mode: interpreter serves, compilation starts
+    first_ms = (time.perf_counter() - t0) * 1e3
+    pend = C.c_int(1)
+    while pend.value and time.perf_counter() - t0 < 60:
+        L.check(L.lib().vexb_jit_pending(C.byref(pend)))
+        time.sleep(0.005)
+    ready_ms = (time.perf_counter() - t0) * 1e3
+    ms_j = time_loop(ctx, gen_expr, steps, 3, ctx.finish) / steps
+    g = lambda ms: 32 * n / (ms * 1e-3) / 1e9
+    out["generic_expression"] = {"expr": "a = (b-c)*(b+c)/d + b*0.5 + c*d", "bytes_per_elem": 32, "n": n,
+                                 "interpreter": {"ms": ms_i, "gbs": g(ms_i), "frac_of_peak": g(ms_i) / peak},
+                                 "specialised_nvrtc": {"ms": ms_j, "gbs": g(ms_j), "frac_of_peak": g(ms_j) / peak},
+                                 "first_call_ms_default_mode": first_ms, "specialised_kernel_ready_after_ms": ready_ms,
+                                 "note": "default mode: the first call is served by the interpreter while NVRTC compiles on a background thread"}
     return out
 
 

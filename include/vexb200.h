@@ -93,8 +93,16 @@ typedef enum {
     VEXB_TERM_VEC = 0,    /* v.ptr: device array of `dtype`, element i of this device slice */
     VEXB_TERM_SCALAR = 1, /* by-value scalar of `dtype` (operations.hpp:168-175)            */
     VEXB_TERM_INDEX = 2,  /* element_index: index_offset + i + v.i64 (element_index.hpp:40-111), type u64 */
-    VEXB_TERM_DSCALAR = 3 /* v.ptr: ONE device-resident value of `dtype`, broadcast to every element.  Lets the
+    VEXB_TERM_DSCALAR = 3,/* v.ptr: ONE device-resident value of `dtype`, broadcast to every element.  Lets the
                              result of vexb_reduce feed the next expression without a host round trip. */
+    VEXB_TERM_SPMV = 4    /* v.ptr: a vexb_spmat (host handle; CSR or hybrid ELL, plain strip); pad[0]: slot of the
+                             VEXB_TERM_VEC holding x.  Element i evaluates to row i of A*x (products added in storage
+                             order, as vexb_spmv does): the sparse product as a *terminal* of the consumer's kernel --
+                             `y = x + A*x` is one launch, y is written once and A*x never goes to memory
+                             (vexcl/sparse/product.hpp:45-130, sparse/csr.hpp:102-132, sparse/ell.hpp:207-265,
+                             spmat/inline_spmv.hpp:68-76).  Expressions with such terminals run on the NVRTC side path
+                             (the row loop is generated into the kernel, specialised to the strip's format and width);
+                             vexb_reduce does not take them. */
 } vexb_term_kind;
 
 typedef struct {
@@ -467,6 +475,9 @@ int vexb_dspmat_get_info(const vexb_dspmat *A, vexb_dspmat_info *info);
 /* Split tables back on the host for parity with csr.inl:70-112 (any pointer may be NULL). */
 int vexb_dspmat_download_split(const vexb_dspmat *A, int64_t *loc_ptr, int64_t *loc_col, void *loc_val,
                                int64_t *rem_ptr, int64_t *rem_col, void *rem_val);
+/* The part's strip for use as a VEXB_TERM_SPMV terminal: set when the part has no ghost columns and its rows are
+ * stored plainly in CSR or hybrid ELL (then row i of the strip is element i of the part's slice); NULL otherwise. */
+int vexb_dspmat_inline_strip(const vexb_dspmat *A, const vexb_spmat **strip);
 void *vexb_dspmat_send_buffer(const vexb_dspmat *A);  /* device, n_send values  */
 void *vexb_dspmat_ghost_buffer(const vexb_dspmat *A); /* device, n_ghost values */
 /* Steps of SpMat::apply, all asynchronous on `stream`: */

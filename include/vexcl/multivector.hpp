@@ -156,7 +156,7 @@ struct multi_assignable {
     VEXCL_MULTI_ASSIGNMENT(^=, XOR) VEXCL_MULTI_ASSIGNMENT(<<=, LSH) VEXCL_MULTI_ASSIGNMENT(>>=, RSH)
 #undef VEXCL_MULTI_ASSIGNMENT
 
-    // Y = A * X and friends: one product per component (multivector.hpp:395-437)
+    // Y = A * X and friends (multivector.hpp:395-437)
     template <class M> const Derived& operator=(const additive_operator<M, multivector<T, N>> &a)  { apply(a, T(1), false); return self(); }
     template <class M> const Derived& operator+=(const additive_operator<M, multivector<T, N>> &a) { apply(a, T(1), true);  return self(); }
     template <class M> const Derived& operator-=(const additive_operator<M, multivector<T, N>> &a) { apply(a, T(-1), true); return self(); }
@@ -164,7 +164,15 @@ struct multi_assignable {
     template <class E, class M> const Derived& operator+=(const multi_mixed<E, M, T, N> &m) { self() += m.expr; apply(m.a, T(1), true);  return self(); }
     template <class E, class M> const Derived& operator-=(const multi_mixed<E, M, T, N> &m) { self() -= m.expr; apply(m.a, T(-1), true); return self(); }
     private:
-        template <class M> void apply(const additive_operator<M, multivector<T, N>> &a, T sign, bool append) {
+        template <class M> void apply(const additive_operator<M, multivector<T, N>> &a, T sign, bool append) { apply_dispatch(a, sign, append, 0); }
+        // an operator that can take all components at once (vex::SpMat: the matrix is streamed once for up to 4 of them) ...
+        template <class M>
+        auto apply_dispatch(const additive_operator<M, multivector<T, N>> &a, T sign, bool append, int)
+            -> decltype(a.A.template apply_multi<N>(a.x, std::declval<Derived&>(), sign, append)) {
+            return a.A.template apply_multi<N>(a.x, self(), sign * a.scale, append);
+        }
+        // ... or one product per component, as the reference does (operations.hpp:876-880)
+        template <class M> void apply_dispatch(const additive_operator<M, multivector<T, N>> &a, T sign, bool append, long) {
             for (size_t i = 0; i < N; ++i) a.A.apply(a.x(i), self()(i), sign * a.scale, append);
         }
 };

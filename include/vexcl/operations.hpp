@@ -79,6 +79,15 @@ struct ir_builder {
         e.term[k].kind = VEXB_TERM_INDEX; e.term[k].dtype = VEXB_U64; e.term[k].v.i64 = offset;
         emit(VEXB_OP_TERM, VEXB_U64, k);
     }
+    /// Row `i` of `A * x` as a terminal (VEXB_TERM_SPMV): A is a plain strip on this device, xptr its x slice.
+    void push_spmv(const vexb_spmat *A, const void *xptr, int dtype) {
+        int xs = new_term();
+        e.term[xs].kind = VEXB_TERM_VEC; e.term[xs].dtype = static_cast<uint8_t>(dtype); e.term[xs].v.ptr = xptr;
+        int k = new_term();
+        e.term[k].kind = VEXB_TERM_SPMV; e.term[k].dtype = static_cast<uint8_t>(dtype); e.term[k].v.ptr = A;
+        e.term[k].pad[0] = static_cast<uint8_t>(xs);
+        emit(VEXB_OP_TERM, dtype, k);
+    }
     void cvt(int from, int to) { if (from != to) emit(VEXB_OP_CVT, to, from); }
 };
 
@@ -299,23 +308,77 @@ struct additive_operator {
 };
 
 namespace detail {
-/// A sum of additive terms, each able to append itself to a vector of value type T.
+/// Does M offer `const vexb_spmat* inline_strip(unsigned device) const` (a strip usable as a VEXB_TERM_SPMV terminal)?
+template <class M, class = void> struct has_inline_strip : std::false_type {};
+template <class M> struct has_inline_strip<M, decltype(void(std::declval<const M&>().inline_strip(0u)))> : std::true_type {};
+
+/// A sum of additive terms, each able to append itself to a vector of value type T -- and, when its operator can be
+/// inlined (vex::SpMat strips without a halo), to lower itself as `scale * (row i of A*x)` into the consumer's kernel.
 template <class T>
 struct additive_terms {
-    typedef std::function<void(vex::vector<T>&, T, bool)> term;
+    struct term {
+        std::function<void(vex::vector<T>&, T, bool)> apply;       ///< y (=|+=) sign * scale * A * x
+        std::function<bool(unsigned)> can_inline;                    ///< on device d
+        std::function<void(ir_builder&, T)> lower;                   ///< pushes sign * scale * (A*x)_i
+        void operator()(vex::vector<T> &y, T sign, bool append) const { apply(y, sign, append); }
+    };
     std::vector<term> terms;
     additive_terms() {}
-    template <class M> additive_terms(const additive_operator<M, vex::vector<T>> &a) {
-        terms.push_back([a](vex::vector<T> &y, T sign, bool append) { a.apply(y, sign, append); });
-    }
+    template <class M> additive_terms(const additive_operator<M, vex::vector<T>> &a) { terms.push_back(make(a)); }
     additive_terms scaled(T s) const {
         additive_terms r;
-        for (auto &t : terms) r.terms.push_back([t, s](vex::vector<T> &y, T sign, bool append) { t(y, sign * s, append); });
+        for (auto &t : terms) {
+            term u;
+            u.apply = [t, s](vex::vector<T> &y, T sign, bool append) { t.apply(y, sign * s, append); };
+            u.can_inline = t.can_inline;
+            u.lower = [t, s](ir_builder &b, T sign) { t.lower(b, sign * s); };
+            r.terms.push_back(u);
+        }
         return r;
     }
     additive_terms& append(const additive_terms &o, T s = 1) {
         for (auto &t : o.scaled(s).terms) terms.push_back(t);
         return *this;
+    }
+    private:
+        template <class M>
+        static typename std::enable_if<has_inline_strip<M>::value, term>::type make(const additive_operator<M, vex::vector<T>> &a) {
+            term t;
+            t.apply = [a](vex::vector<T> &y, T sign, bool append) { a.apply(y, sign, append); };
+            t.can_inline = [a](unsigned d) { return a.A.inline_strip(d) != nullptr; };
+            t.lower = [a](ir_builder &b, T sign) {
+                const int dt = dtype_of<T>::value;
+                b.push_scalar(static_cast<T>(sign * a.scale));
+                b.push_spmv(a.A.inline_strip(b.part), a.x(b.part).raw(), dt);
+                b.emit(VEXB_OP_MUL, dt);
+            };
+            return t;
+        }
+        template <class M>
+        static typename std::enable_if<!has_inline_strip<M>::value, term>::type make(const additive_operator<M, vex::vector<T>> &a) {
+            term t;
+            t.apply = [a](vex::vector<T> &y, T sign, bool append) { a.apply(y, sign, append); };
+            t.can_inline = [](unsigned) { return false; };
+            t.lower = [](ir_builder&, T) {};
+            return t;
+        }
+};
+
+/// `expr + s1*(A1*x1) + s2*(A2*x2) ...` as ONE expression: the vector part followed by the inlined products, added in the
+/// order the unfused path applies them (same bits), evaluated by a single generated kernel.
+template <class E, class T>
+struct fused_mixed : vector_expr_tag {
+    static const bool hold_by_reference = false;
+    typedef T value_type;
+    const E &expr; const additive_terms<T> &terms; T sign;
+    fused_mixed(const E &e, const additive_terms<T> &t, T sign) : expr(e), terms(t), sign(sign) {}
+    void props(expr_props &p) const { expr.props(p); }
+    int lower(ir_builder &b) const {
+        const int dt = dtype_of<T>::value;
+        const int et = expr.lower(b);
+        b.cvt(et, dt);
+        for (auto &t : terms.terms) { t.lower(b, sign); b.emit(VEXB_OP_ADD, dt); }
+        return dt;
     }
 };
 } // namespace detail

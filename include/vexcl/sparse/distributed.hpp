@@ -41,6 +41,9 @@ class distributed {
             A.apply(x, y, alpha, append);
         }
 
+        /// Device d's strip when a generated kernel can walk its rows (no halo on that device), else NULL.
+        const vexb_spmat* inline_strip(unsigned d) const { return A.inline_strip(d); }
+
         template <class Expr>
         friend typename std::enable_if<is_vector_expr<Expr>::value, matrix_vector_product<distributed, Expr> >::type
         operator*(const distributed &A, const Expr &x) { return matrix_vector_product<distributed, Expr>(A, x); }

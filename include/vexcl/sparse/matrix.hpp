@@ -52,6 +52,13 @@ class single_device_matrix {
             VEXB_CHECKED(vexb_spmv(q[0].ordinal(), q[0].raw(), A.get(), x(0).raw(), y(0).raw(), static_cast<double>(alpha), append));
         }
 
+        /// The strip when a generated kernel can walk its rows (CSR / hybrid ELL), else NULL.
+        const vexb_spmat* inline_strip(unsigned = 0) const {
+            vexb_spmat_info i;
+            if (!A || vexb_spmat_get_info(A.get(), &i) != VEXB_OK) return nullptr;
+            return (i.fmt == VEXB_FMT_CSR || i.fmt == VEXB_FMT_HELL) ? A.get() : nullptr;
+        }
+
         template <class Expr>
         friend typename std::enable_if<is_vector_expr<Expr>::value, matrix_vector_product<single_device_matrix, Expr> >::type
         operator*(const single_device_matrix &A, const Expr &x) { return matrix_vector_product<single_device_matrix, Expr>(A, x); }

@@ -88,6 +88,31 @@ class SpMat {
             VEXB_CHECKED(vexb_dspmat_apply(nd, cm, mtx.data(), streams.data(), xs.data(), ys.data(), static_cast<double>(alpha), append));
         }
 
+        /// Y(i) = alpha * A * X(i) (or +=) for all N components; the matrix is read once per group of up to four components
+        /// when the strips have no halo (vexb_dspmat_apply_multi; the reference multiplies component by component).
+        template <size_t N, class X, class Y>
+        void apply_multi(const X &x, Y &y, scalar_type alpha = 1, bool append = false) const {
+            const int nd = static_cast<int>(queue.size());
+            std::vector<const void*> xs(nd * N); std::vector<void*> ys(nd * N), streams(nd);
+            for (size_t i = 0; i < N; ++i)
+                precondition(x(i).size() == ncols && y(i).size() == nrows, "SpMat::apply: vector sizes do not match the matrix");
+            for (int d = 0; d < nd; ++d) {
+                streams[d] = queue[d].raw();
+                for (size_t i = 0; i < N; ++i) { xs[d * N + i] = x(i)(d).raw(); ys[d * N + i] = y(i)(d).raw(); }
+            }
+            vexb_comm *const *cm = (comms && !comms->comms.empty()) ? comms->comms.data() : nullptr;
+            VEXB_CHECKED(vexb_dspmat_apply_multi(nd, cm, mtx.data(), streams.data(), static_cast<int>(N), xs.data(), ys.data(),
+                                                 static_cast<double>(alpha), append));
+        }
+
+        /// The strip of device d when it can be inlined into an expression kernel (no halo, plain CSR / hybrid ELL), else NULL.
+        const vexb_spmat* inline_strip(unsigned d) const {
+            const vexb_spmat *s = nullptr;
+            if (d < mtx.size() && mtx[d]) vexb_dspmat_inline_strip(mtx[d], &s);
+            return s;
+        }
+        bool inlinable() const { for (unsigned d = 0; d < mtx.size(); ++d) if (!inline_strip(d)) return false; return !mtx.empty(); }
+
         size_t rows() const { return nrows; }
         size_t cols() const { return ncols; }
         size_t nonzeros() const { return nnz; }
@@ -116,9 +141,9 @@ operator*(const SpMat<val_t, col_t, idx_t> &A, const vector<val_t> &x) {
 
 /// `A * x` as a terminal of any vector expression (vexcl/spmat/inline_spmv.hpp:42-76), e.g.
 ///     eps = sum(fabs(f - vex::make_inline(A * x)));
-/// The reference restricts this to one device because it inlines the row loop into the consumer's kernel; here the
-/// product is evaluated by the SpMV kernels into a temporary when the enclosing expression is launched, so it also
-/// works across devices.
+/// As in the reference, the row loop is generated into the consumer's kernel (VEXB_TERM_SPMV, NVRTC) whenever the
+/// strips have no halo (one device, or a block-diagonal matrix); otherwise -- which the reference forbids -- the product is
+/// evaluated by the SpMV kernels into a temporary when the enclosing expression is launched.
 template <class M, class V>
 struct inline_spmv : vector_expr_tag {
     static const bool hold_by_reference = false;
@@ -127,11 +152,18 @@ struct inline_spmv : vector_expr_tag {
     mutable std::shared_ptr<vex::vector<value_type>> y;
     inline_spmv(const M &A, const V &x) : A(A), x(x) {}
     void props(detail::expr_props &p) const {
+        fused = std::is_floating_point<value_type>::value && A.inlinable() && x.size() == A.cols();
+        if (fused) { p.see(x.queue_list(), vex::partition(A.rows(), x.queue_list()), A.rows()); return; }   // the row loop goes into the consumer's kernel
         if (!y || y->size() != A.rows()) y = std::make_shared<vex::vector<value_type>>(x.queue_list(), A.rows());
         A.apply(x, *y, 1, false);
         y->props(p);
     }
-    int lower(detail::ir_builder &b) const { return y->lower(b); }
+    int lower(detail::ir_builder &b) const {
+        if (!fused) return y->lower(b);
+        b.push_spmv(A.inline_strip(b.part), x(b.part).raw(), dtype_of<value_type>::value);
+        return dtype_of<value_type>::value;
+    }
+    mutable bool fused = false;
 };
 
 template <typename val_t, typename col_t, typename idx_t>

@@ -205,9 +205,20 @@ class vector : public vector_expr_tag {
         const vector& operator+=(const detail::additive_terms<T> &a) { apply_terms(a, T(1), true);  return *this; }
         const vector& operator-=(const detail::additive_terms<T> &a) { apply_terms(a, T(-1), true); return *this; }
         // vector part first, then each additive term appended (vector.hpp:758-763)
-        template <class E> const vector& operator=(const mixed_expression<E, T> &m)  { *this = m.expr;  apply_terms(m.terms, T(1), true);  return *this; }
-        template <class E> const vector& operator+=(const mixed_expression<E, T> &m) { *this += m.expr; apply_terms(m.terms, T(1), true);  return *this; }
-        template <class E> const vector& operator-=(const mixed_expression<E, T> &m) { *this -= m.expr; apply_terms(m.terms, T(-1), true); return *this; }
+        // When every product can be inlined (strips without a halo) the whole right-hand side is ONE generated kernel:
+        // `y = x + A*x` reads A and x once and writes y once (sparse/product.hpp:45-130 is the reference's fused form).
+        template <class E> const vector& operator=(const mixed_expression<E, T> &m) {
+            if (inlinable(m.terms)) { detail::assign_expression<assign::SET>(*this, detail::fused_mixed<E, T>(m.expr, m.terms, T(1))); return *this; }
+            *this = m.expr;  apply_terms(m.terms, T(1), true);  return *this;
+        }
+        template <class E> const vector& operator+=(const mixed_expression<E, T> &m) {
+            if (inlinable(m.terms)) { detail::assign_expression<assign::ADD>(*this, detail::fused_mixed<E, T>(m.expr, m.terms, T(1))); return *this; }
+            *this += m.expr; apply_terms(m.terms, T(1), true);  return *this;
+        }
+        template <class E> const vector& operator-=(const mixed_expression<E, T> &m) {
+            if (inlinable(m.terms)) { detail::assign_expression<assign::SUB>(*this, detail::fused_mixed<E, T>(m.expr, m.terms, T(1))); return *this; }
+            *this -= m.expr; apply_terms(m.terms, T(-1), true); return *this;
+        }
 
         // ---- expression terminal protocol -------------------------------------------------
         int lower(detail::ir_builder &b) const { b.push_vec(buf[b.part].raw(), dtype_of<T>::value); return dtype_of<T>::value; }
@@ -243,6 +254,11 @@ class vector : public vector_expr_tag {
         }
         void apply_terms(const detail::additive_terms<T> &a, T sign, bool append) {
             for (auto &t : a.terms) { t(*this, sign, append); append = true; }
+        }
+        bool inlinable(const detail::additive_terms<T> &a) const {
+            if (a.terms.empty() || a.terms.size() > 6 || !std::is_floating_point<T>::value) return false;
+            for (auto &t : a.terms) for (unsigned d = 0; d < queue.size(); ++d) if (!t.can_inline(d)) return false;
+            return true;
         }
 };
 

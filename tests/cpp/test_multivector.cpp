@@ -239,6 +239,35 @@ BOOST_AUTO_TEST_CASE(multivector_product)                 // spmv.cpp:262-307
     });
 }
 
+// SpMat * multivector<double,4> on one slice: all four products come out of ONE pass over the matrix (hell_multi_kernel),
+// with the same bits as four single products.
+BOOST_AUTO_TEST_CASE(multivector_product_reads_the_matrix_once)
+{
+    const size_t n = 4096, m = 4;
+    std::vector<vex::command_queue> queue(1, ctx.queue(0));
+    std::vector<size_t> row, col; std::vector<double> val;
+    random_matrix(n, n, 12, row, col, val);
+    std::vector<double> x = random_vector<double>(n * m);
+    vex::SpMat<double> A(queue, n, n, row.data(), col.data(), val.data());
+    vex::multivector<double, m> X(queue, x), Y(queue, n), Z(queue, n);
+    uint64_t l0 = 0, l1 = 0;
+    vexb_launch_count(&l0);
+    Y = A * X;
+    vexb_launch_count(&l1);
+    if (A.info().loc.fmt == VEXB_FMT_HELL) BOOST_CHECK_EQUAL(l1 - l0, 1u);
+    for (size_t i = 0; i < m; ++i) Z(i) = A * X(i);
+    std::vector<double> y(n * m), z(n * m);
+    vex::copy(Y, y); vex::copy(Z, z);
+    size_t diff = 0;
+    for (size_t k = 0; k < n * m; ++k) diff += y[k] != z[k];
+    BOOST_CHECK_EQUAL(diff, 0u);
+    Y += 0.5 * (A * X);
+    for (size_t i = 0; i < m; ++i) Z(i) += 0.5 * (A * X(i));
+    vex::copy(Y, y); vex::copy(Z, z);
+    for (size_t k = 0; k < n * m; ++k) diff += y[k] != z[k];
+    BOOST_CHECK_EQUAL(diff, 0u);
+}
+
 BOOST_AUTO_TEST_CASE(inline_multivector_product)          // spmv.cpp:309-343
 {
     const size_t n = 1024, m = 2;

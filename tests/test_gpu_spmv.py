@@ -194,3 +194,54 @@ def test_split_tables_match_reference(ctx3):
     x, y = vx.vector(ctx3, X), vx.vector(ctx3, n)
     y.assign(A * x)
     assert close(y.read(), oracle.spmat_apply(part, part, row, col, val, X))
+
+
+@pytest.mark.parametrize("fmt", [L.FMT_HELL, L.FMT_CSR])
+def test_product_inlined_into_the_consumer_kernel(ctx1, fmt):
+    """`y = x + A*x`, `y = z - 0.5*(A*x) + 2*(B*w)` and make_inline(A*x) inside any expression run as ONE generated kernel
+    (VEXB_TERM_SPMV: sparse/product.hpp:45-130, spmat/inline_spmv.hpp:68-76); same bits as the unfused composition."""
+    for row, col, val in (oracle.poisson(2, 70), oracle.random_matrix(3000, 3000, 11, seed=9), oracle.tridiagonal(2000)):
+        n = row.size - 1
+        X, Z = oracle.uniform_real(3, n), oracle.uniform_real(4, n)
+        A = vx.SpMat(ctx1, n, n, row, col, val, fmt)
+        x, z, y, y2 = vx.vector(ctx1, X), vx.vector(ctx1, Z), vx.vector(ctx1, n), vx.vector(ctx1, n)
+        ax = oracle.csr_spmv(row, col, val, X)
+        n0 = vx.launch_count()
+        y.assign(x + A * x)
+        assert vx.launch_count() - n0 == 1                                   # one kernel: no temporary, no second pass over y
+        assert np.array_equal(y.read(), X + ax)
+        ctx1.fuse_products = False
+        try:
+            y2.assign(x + A * x)                                             # the unfused path: vector part, then y += A*x
+        finally:
+            ctx1.fuse_products = True
+        assert np.array_equal(y.read(), y2.read())
+        n0 = vx.launch_count()
+        y.assign(z - 0.5 * (A * x) + 2.0 * (A * z))
+        assert vx.launch_count() - n0 == 1
+        az = oracle.csr_spmv(row, col, val, Z)
+        assert np.array_equal(y.read(), (Z + (-0.5) * ax) + 2.0 * az)
+        y += x + A * x
+        mag = oracle.csr_absrow(row, col, val, X) + np.abs(X) + np.abs(Z) + 2 * oracle.csr_absrow(row, col, val, Z)
+        assert np.all(np.abs(y.read() - (((Z - 0.5 * ax) + 2.0 * az) + (X + ax))) <= 1e-10 * mag)
+        # as a terminal of any expression
+        n0 = vx.launch_count()
+        y.assign(vx.sin(vx.make_inline(A * x)) * z + 1.0)
+        assert vx.launch_count() - n0 == 1
+        assert np.allclose(y.read(), np.sin(ax) * Z + 1.0, rtol=1e-14, atol=1e-14)
+        # reductions evaluate the inlined expression into a temporary first
+        s = vx.Reductor(ctx1, np.float64, L.SUM)(z - vx.make_inline(A * x))
+        assert abs(s - oracle.kahan_sum(Z - ax)) <= 1e-10 * np.sum(np.abs(Z) + np.abs(ax))
+
+
+def test_inline_product_falls_back_to_a_temporary_with_a_halo(ctx2):
+    row, col, val = oracle.poisson(2, 60)
+    n = row.size - 1
+    X = oracle.uniform_real(5, n)
+    A = vx.SpMat(ctx2, n, n, row, col, val)
+    x, y = vx.vector(ctx2, X), vx.vector(ctx2, n)
+    y.assign(x + A * x)
+    want = oracle.csr_spmv(row, col, val, X)
+    assert np.all(np.abs(y.read() - (X + want)) <= 1e-10 * (np.abs(X) + oracle.csr_absrow(row, col, val, X)))
+    y.assign(2.0 * vx.make_inline(A * x) - x)
+    assert np.all(np.abs(y.read() - (2.0 * want - X)) <= 1e-10 * (np.abs(X) + 2 * oracle.csr_absrow(row, col, val, X)))

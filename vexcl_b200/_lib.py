@@ -16,7 +16,7 @@ ERR_CUDA, ERR_INVALID, ERR_NCCL, ERR_UNSUPPORTED, ERR_NOMEM, ERR_PEER = range(1,
 F64, F32, I32, U32, I64, U64 = range(6)
 SET, ADD, SUB, MUL, DIV, MOD, AND, OR, XOR, LSH, RSH = range(11)
 SUM, SUM_KAHAN, MAX, MIN, MINMAX = range(5)
-TERM_VEC, TERM_SCALAR, TERM_INDEX, TERM_DSCALAR = range(4)
+TERM_VEC, TERM_SCALAR, TERM_INDEX, TERM_DSCALAR, TERM_SPMV = range(5)
 FMT_AUTO, FMT_CSR, FMT_HELL, FMT_PATTERNS = range(4)
 MAX_TERMS, MAX_CODE, MAX_STACK = 16, 64, 12
 
@@ -174,6 +174,7 @@ def lib():
         "vexb_dspmat_halo_disconnect": ([vp], i),
         "vexb_dspmat_apply_dot": ([i, P(vp), P(vp), P(vp), P(vp), d, i, P(vp), P(vp), P(vp)], i),
         "vexb_peer_fault": ([P(C.c_uint64), i], i),
+        "vexb_dspmat_inline_strip": ([vp, P(vp)], i),
         "vexb_spmv_multi": ([i, vp, vp, i, P(vp), P(vp), d, i], i),
         "vexb_dspmat_apply_multi": ([i, P(vp), P(vp), P(vp), i, P(vp), P(vp), d, i], i),
         "vexb_jit_pending": ([P(i)], i),

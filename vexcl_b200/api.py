@@ -343,12 +343,13 @@ class _Lowering:
         self.size = None
         self.ctx = None
 
-    def term(self, kind, dtype, **kw) -> int:
+    def term(self, kind, dtype, pad0: int = 0, **kw) -> int:
         k = self.e.n_terms
         if k >= L.MAX_TERMS:
             raise ValueError("expression has too many terminals")
         t = self.e.term[k]
         t.kind, t.dtype = kind, dtype
+        t.pad[0] = pad0
         for name, v in kw.items():
             setattr(t.v, name, v)
         self.e.n_terms = k + 1
@@ -373,6 +374,16 @@ class _Lowering:
             elif n.n != self.size:
                 raise ValueError("vectors of different sizes in one expression")     # VEXCL_CHECK_SIZES, operations.hpp:1824-1840
             self.emit("TERM", n.dtype, self.term(L.TERM_VEC, n.dtype, ptr=n.bufs[self.part].value or 0))
+        elif isinstance(n, InlineSpMV):
+            if self.size is None:
+                self.size, self.ctx = n.A.n, n.A.ctx
+            strip = n.strip(self.part)
+            if strip is not None:
+                # row i of A*x as a terminal: the row loop is generated into this expression's kernel (VEXB_TERM_SPMV)
+                xs = self.term(L.TERM_VEC, n.dtype, ptr=n.x.bufs[self.part].value or 0)
+                self.emit("TERM", n.dtype, self.term(L.TERM_SPMV, n.dtype, pad0=xs, ptr=strip))
+            else:
+                self.lower(n.temporary())
         elif isinstance(n, Scalar):
             field = {L.F64: "f64", L.F32: "f32", L.I32: "i32", L.U32: "u32", L.I64: "i64", L.U64: "u64"}[n.dtype]
             self.emit("TERM", n.dtype, self.term(L.TERM_SCALAR, n.dtype, **{field: n.value}))
@@ -406,7 +417,7 @@ class _Lowering:
 
 
 def _has_call(n) -> bool:
-    if isinstance(n, Call):
+    if isinstance(n, (Call, InlineSpMV)):
         return True
     kids = [getattr(n, c, None) for c in ("a", "b", "cond")] + list(getattr(n, "args", []))
     return any(isinstance(k, Node) and _has_call(k) for k in kids)
@@ -426,6 +437,8 @@ def _find_props(n: Node):
     """(ctx, size) of the first vector terminal (get_expression_properties, operations.hpp:1411)."""
     if isinstance(n, vector):
         return n.ctx, n.n
+    if isinstance(n, InlineSpMV):
+        return n.A.ctx, n.A.n
     for child in ("a", "b", "cond"):
         c = getattr(n, child, None)
         if isinstance(c, Node):
@@ -437,6 +450,48 @@ def _find_props(n: Node):
         if r:
             return r
     return None
+
+
+# ------------------------------------------------------------------------------------------- inlined sparse products
+class InlineSpMV(Node):
+    """`A * x` as a terminal of a vector expression: vex::make_inline(A * x) (spmat/inline_spmv.hpp:68-76) and the
+    vex::sparse product terminal (sparse/product.hpp:45-130).  When the strips have no halo the row loop is generated into
+    the consumer's kernel (VEXB_TERM_SPMV); otherwise the product is evaluated into a temporary when the expression is
+    lowered.  A fresh node per use."""
+
+    def __init__(self, A, x):
+        if x.n != A.m:
+            raise ValueError("inline product: vector size does not match the matrix")
+        self.A, self.x, self.dtype = A, x, x.dtype
+        self._tmp = None
+
+    def strip(self, part):
+        if not _is_float(self.dtype) or not hasattr(self.A, "parts"):
+            return None
+        h = C.c_void_p()
+        L.check(L.lib().vexb_dspmat_inline_strip(self.A.parts[part], C.byref(h)))
+        if not h.value:
+            return None
+        # all or nothing: an expression is lowered once per slot, and every slot must see the same kind of terminal
+        for k in self.A.ctx.local:
+            hk = C.c_void_p()
+            L.check(L.lib().vexb_dspmat_inline_strip(self.A.parts[k], C.byref(hk)))
+            if not hk.value:
+                return None
+        return h.value
+
+    def temporary(self):
+        if self._tmp is None:
+            self._tmp = vector(self.A.ctx, self.A.n, self.x.np_dtype)
+            self.A.apply(self.x, self._tmp, 1.0, False)
+        return self._tmp
+
+
+def make_inline(term):
+    """vex::make_inline(A * x): the (unscaled) product as an expression terminal."""
+    if not isinstance(term, SpMVTerm) or term.scale != 1.0:
+        raise ValueError("make_inline: scale the inlined product inside the expression instead")
+    return InlineSpMV(term.A, term.x)
 
 
 # ------------------------------------------------------------------------------------------- SpMV additive terms
@@ -601,6 +656,16 @@ class vector(Node):
     def _assign_mixed(self, op: int, m: Mixed):
         if op not in (L.SET, L.ADD, L.SUB):
             raise TypeError("additive operators only combine with =, += and -=")
+        # every product inlinable (strips without a halo): the whole right-hand side is ONE generated kernel, e.g. `y = x + A*x`
+        # reads A and x once and writes y once.  Same operation order as the unfused path below for `=`.
+        if (m.vec is not None or len(m.terms) > 1) and len(m.terms) <= 6 and _is_float(self.dtype) and getattr(self.ctx, "fuse_products", True):
+            nodes = [InlineSpMV(t.A, t.x) if isinstance(t.A, SpMat) and isinstance(t.x, vector) and t.x.n == t.A.m else None for t in m.terms]
+            if all(nd is not None and nd.strip(self.ctx.local[0]) is not None for nd in nodes):
+                expr = m.vec
+                for t, nd in zip(m.terms, nodes):
+                    prod = Binary("MUL", Scalar(float(t.scale), self.dtype), nd)
+                    expr = prod if expr is None else Binary("ADD", wrap(expr), prod)
+                return self._assign(op, expr)
         sign = -1.0 if op == L.SUB else 1.0
         append = op != L.SET
         if m.vec is not None:
@@ -912,6 +977,23 @@ def _spmat_apply_dot(self, x: "vector", y: "vector", out: "DeviceScalar", dot_wi
 
 
 SpMat.apply_dot = _spmat_apply_dot
+
+
+def _spmat_apply_multi(self, xs, ys, alpha: float = 1.0, append: bool = False):
+    """ys[r] (=|+=) alpha*A*xs[r] for every r: vex::SpMat * vex::multivector.  Strips without a halo read the matrix once per
+    group of up to four vectors (vexb_dspmat_apply_multi); the reference multiplies component by component."""
+    ctx, nrhs = self.ctx, len(xs)
+    if nrhs != len(ys) or nrhs < 1 or any(x.n != self.m for x in xs) or any(y.n != self.n for y in ys):
+        raise ValueError("SpMat::apply_multi: vector counts or sizes do not match the matrix")
+    xa = (C.c_void_p * (len(ctx.local) * nrhs))(*[xs[r].bufs[k] for k in ctx.local for r in range(nrhs)])
+    ya = (C.c_void_p * (len(ctx.local) * nrhs))(*[ys[r].bufs[k] for k in ctx.local for r in range(nrhs)])
+    comms = ctx._arr(ctx.comms) if ctx.comms is not None else None
+    L.check(L.lib().vexb_dspmat_apply_multi(len(ctx.local), comms, ctx._arr(self.parts), ctx._arr(ctx.streams), nrhs, xa, ya,
+                                            float(alpha), int(append)))
+    return ys
+
+
+SpMat.apply_multi = _spmat_apply_multi
 
 
 class SpMatCCSR:

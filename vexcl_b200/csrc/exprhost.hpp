@@ -72,6 +72,11 @@ inline void convert_scalar_term(vexb_term &t, int to) {
     t.dtype = (uint8_t)to;
 }
 
+inline bool expr_has_spmv(const vexb_expr &e) {
+    for (int k = 0; k < e.n_terms; ++k) if (e.term[k].kind == VEXB_TERM_SPMV) return true;
+    return false;
+}
+
 inline bool expr_has_call(const vexb_expr &e) {
     for (int pc = 0; pc < e.n_code; ++pc) if (e.code[pc].op == VEXB_OP_CALL) return true;
     return false;
@@ -95,9 +100,14 @@ inline int normalize_expr(const vexb_expr *in, vexb_expr *out, bool need_ptrs = 
     VEXB_CHECK(in->n_code >= 1 && in->n_code <= VEXB_MAX_CODE, "n_code=%d out of range", in->n_code);
     for (int k = 0; k < in->n_terms; ++k) {
         const vexb_term &t = in->term[k];
-        VEXB_CHECK(t.kind <= VEXB_TERM_DSCALAR, "term %d: bad kind %d", k, (int)t.kind);
+        VEXB_CHECK(t.kind <= VEXB_TERM_SPMV, "term %d: bad kind %d", k, (int)t.kind);
         VEXB_CHECK(t.dtype <= VEXB_U64, "term %d: bad dtype %d", k, (int)t.dtype);
         VEXB_CHECK(!need_ptrs || (t.kind != VEXB_TERM_VEC && t.kind != VEXB_TERM_DSCALAR) || t.v.ptr != nullptr, "term %d: NULL device pointer", k);
+        if (t.kind == VEXB_TERM_SPMV) {
+            VEXB_CHECK(t.v.ptr != nullptr, "term %d: NULL matrix handle", k);
+            VEXB_CHECK(t.pad[0] < in->n_terms && in->term[t.pad[0]].kind == VEXB_TERM_VEC && in->term[t.pad[0]].dtype == t.dtype,
+                       "term %d: the sparse product's x must be a vector terminal of the matrix's value type", k);
+        }
     }
     // 1. de-duplicate vector terminals (same pointer, same dtype) and drop unused ones.
     int remap[VEXB_MAX_TERMS];
@@ -122,6 +132,22 @@ inline int normalize_expr(const vexb_expr *in, vexb_expr *out, bool need_ptrs = 
             if (slot < 0 && (t.kind == VEXB_TERM_VEC || t.kind == VEXB_TERM_DSCALAR)) {
                 for (int j = 0; j < out->n_terms; ++j)
                     if (out->term[j].kind == t.kind && out->term[j].v.ptr == t.v.ptr && out->term[j].dtype == t.dtype) { slot = j; break; }
+            }
+            if (slot < 0 && t.kind == VEXB_TERM_SPMV) {
+                // the x it multiplies: an ordinary vector terminal (shared with other uses of the same vector)
+                const vexb_term &xt = in->term[t.pad[0]];
+                int xs = remap[t.pad[0]];
+                for (int j = 0; xs < 0 && j < out->n_terms; ++j)
+                    if (out->term[j].kind == VEXB_TERM_VEC && out->term[j].v.ptr == xt.v.ptr && out->term[j].dtype == xt.dtype) xs = j;
+                if (xs < 0) { VEXB_CHECK(out->n_terms < VEXB_MAX_TERMS, "too many terminals"); xs = out->n_terms++; out->term[xs] = xt; memset(out->term[xs].pad, 0, sizeof(xt.pad)); }
+                remap[t.pad[0]] = xs;
+                for (int j = 0; j < out->n_terms; ++j)
+                    if (out->term[j].kind == VEXB_TERM_SPMV && out->term[j].v.ptr == t.v.ptr && out->term[j].pad[0] == xs) { slot = j; break; }
+                if (slot < 0) {
+                    VEXB_CHECK(out->n_terms < VEXB_MAX_TERMS, "too many terminals");
+                    slot = out->n_terms++; out->term[slot] = t; memset(out->term[slot].pad, 0, sizeof(t.pad));
+                    out->term[slot].pad[0] = (uint8_t)xs;
+                }
             }
             if (slot < 0) { slot = out->n_terms++; out->term[slot] = t; memset(out->term[slot].pad, 0, sizeof(t.pad)); }
             remap[ins.arg] = slot;
@@ -171,8 +197,11 @@ inline int normalize_expr(const vexb_expr *in, vexb_expr *out, bool need_ptrs = 
     // 3. compact away scalar slots orphaned by folding
     bool used[VEXB_MAX_TERMS] = {false};
     for (int pc = 0; pc < out->n_code; ++pc) if (out->code[pc].op == VEXB_OP_TERM) used[out->code[pc].arg] = true;
+    for (int k = 0; k < out->n_terms; ++k) if (used[k] && out->term[k].kind == VEXB_TERM_SPMV) used[out->term[k].pad[0]] = true;
     int newslot[VEXB_MAX_TERMS]; int n = 0;
-    for (int k = 0; k < out->n_terms; ++k) { newslot[k] = used[k] ? n : -1; if (used[k]) { if (n != k) out->term[n] = out->term[k]; ++n; } }
+    for (int k = 0; k < out->n_terms; ++k) newslot[k] = used[k] ? n++ : -1;
+    for (int k = 0; k < out->n_terms; ++k) if (used[k] && out->term[k].kind == VEXB_TERM_SPMV) out->term[k].pad[0] = (uint8_t)newslot[out->term[k].pad[0]];
+    for (int k = 0; k < out->n_terms; ++k) if (used[k] && newslot[k] != k) out->term[newslot[k]] = out->term[k];
     for (int k = n; k < out->n_terms; ++k) memset(&out->term[k], 0, sizeof(vexb_term));
     out->n_terms = n;
     for (int pc = 0; pc < out->n_code; ++pc) if (out->code[pc].op == VEXB_OP_TERM) out->code[pc].arg = (uint16_t)newslot[out->code[pc].arg];

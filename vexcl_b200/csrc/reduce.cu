@@ -456,9 +456,9 @@ extern "C" int vexb_reduce_all(int dev, void *stream, const vexb_expr *expr, int
     if (op == VEXB_SUM_KAHAN && !dtype_is_float(dtype)) op = VEXB_SUM;
     vexb_expr e;
     VEXB_TRY(normalize_expr(expr, &e, n != 0));
-    if (expr_has_call(e))
-        VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "reductions of expressions that call user functions are evaluated into a temporary first "
-                                        "(the front ends do this); vexb_reduce itself has no run-time compiled form");
+    if (expr_has_call(e) || expr_has_spmv(e))
+        VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "reductions of expressions that call user functions or inline a sparse product are evaluated into a "
+                                        "temporary first (the front ends do this); vexb_reduce itself has no run-time compiled form");
     if (n == 0) {                                                               // reductor.hpp:318-321
         VEXB_TRY(vexb_reduce_identity(dev, stream, dtype, op, d_result));
         return pa.nranks > 1 ? vexb_peer_allreduce(peer, stream, d_result, dtype, op) : VEXB_OK;
@@ -577,7 +577,7 @@ extern "C" int vexb_reduce_multi(int dev, void *stream, const vexb_expr *expr, i
     if (peer && peer->nranks > 1) { VEXB_CHECK(peer->dev == dev, "peer group lives on device %d, not %d", peer->dev, dev); pa = peer->args(); }
     vexb_expr e;
     VEXB_TRY(normalize_expr(expr, &e, n != 0));
-    if (expr_has_call(e)) VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "reductions of expressions that call user functions are evaluated into a temporary first");
+    if (expr_has_call(e) || expr_has_spmv(e)) VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "reductions of expressions that call user functions or inline a sparse product are evaluated into a temporary first");
     const size_t es = dtype_size(dtype);
     if (n == 0) {
         for (int k = 0; k < nops; ++k) {

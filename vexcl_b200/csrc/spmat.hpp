@@ -25,7 +25,17 @@ struct vexb_spmat {
     size_t y_offset = 0;           // y index of stored row 0 when the strip covers a contiguous row range
     size_t nrows_stored = 0;       // rows held in the arrays (== nrows unless row_ids)
     size_t device_bytes = 0;
+    void *d_desc = nullptr;        // device copy of vexb::SpmvDesc (what a generated kernel needs to walk the rows); see jit.cu
 };
+
+namespace vexb {
+// Everything a kernel generated for a VEXB_TERM_SPMV terminal reads about the strip (uniform loads through one pointer).
+struct SpmvDesc {
+    const void *ell_col; const void *ell_val; const int *tail_ptr; const int *tail_col; const void *tail_val;
+    const int *rowptr; const int *col; const void *val;
+    unsigned long long pitch; int width; int shift;
+};
+}
 
 namespace vexb {
 // Build a strip from 32-bit host CSR.  row_ids (optional) maps stored row r to its y index;

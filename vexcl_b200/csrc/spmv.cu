@@ -901,6 +901,16 @@ int vexb::spmat_from_csr(int dev, size_t nrows, size_t ncols, std::vector<int> &
         std::vector<int> ids(*row_ids);
         st = upload(ids, 0, (void **)&A->row_ids, &A->device_bytes);
     }
+    if (st == VEXB_OK && (A->fmt == VEXB_FMT_CSR || A->fmt == VEXB_FMT_HELL)) {
+        SpmvDesc d; memset(&d, 0, sizeof(d));
+        d.ell_col = A->ell_col16 ? (const void *)A->ell_col16 : (const void *)A->ell_col; d.ell_val = A->ell_val;
+        d.tail_ptr = A->tail_ptr; d.tail_col = A->tail_col; d.tail_val = A->tail_val;
+        d.rowptr = A->rowptr; d.col = A->col; d.val = A->val;
+        d.pitch = A->ell_pitch; d.width = (int)A->ell_width; d.shift = A->ell_shift;
+        cudaError_t e = cudaMalloc(&A->d_desc, sizeof(d));
+        if (e == cudaSuccess) e = cudaMemcpy(A->d_desc, &d, sizeof(d), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error(__FILE__, __LINE__, "strip descriptor upload failed: %s", cudaGetErrorString(e)); st = VEXB_ERR_CUDA; }
+    }
     if (st != VEXB_OK) { vexb_spmat_destroy(A); return st; }
     *out = A;
     return VEXB_OK;
@@ -942,7 +952,7 @@ extern "C" int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols
 extern "C" int vexb_spmat_destroy(vexb_spmat *A) {
     if (!A) return VEXB_OK;
     DeviceGuard g(A->dev);
-    cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile); cudaFree(A->wtile);
+    cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile); cudaFree(A->wtile); cudaFree(A->d_desc);
     vexb_ccsr_destroy(A->patterns);
     cudaFree(A->row_ids); cudaFree(A->ell_col); cudaFree(A->ell_col16); cudaFree(A->ell_val); cudaFree(A->tail_ptr); cudaFree(A->tail_col); cudaFree(A->tail_val);
     delete A;
