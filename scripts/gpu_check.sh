@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -120 > gpurun_out/pytest_gpu.log
 tail -8 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 tail -c 600 gpurun_out/bench_n1.err

@@ -2,6 +2,9 @@
 // (tests/context_setup.hpp, tests/random_vector.hpp, tests/random_matrix.hpp).
 #pragma once
 #include <cmath>
+#include <csignal>
+#include <execinfo.h>
+#include <unistd.h>
 #include <cstdlib>
 #include <ctime>
 #include <functional>
@@ -90,7 +93,19 @@ template <class V1, class V2, class V3, class F> void check_sample(const V1 &v1,
     for (size_t i = 0; i < SAMPLE_SIZE; ++i) { size_t idx = rand() % v1.size(); f(idx, v1[idx], v2[idx], v3[idx]); }
 }
 
+// A crash (also one during static destruction after main) leaves a backtrace on stderr instead of a bare status 139.
+inline void crash_backtrace(int sig) {
+    void *bt[64];
+    const int n = backtrace(bt, 64);
+    const char msg[] = "fatal signal, backtrace:\n";
+    if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    backtrace_symbols_fd(bt, n, 2);
+    _exit(128 + sig);
+}
+
 int main(int argc, char **argv) {
+    std::signal(SIGSEGV, crash_backtrace);
+    std::signal(SIGABRT, crash_backtrace);
     unsigned seed = argc > 1 ? std::atoi(argv[1]) : static_cast<unsigned>(time(0));
     std::cout << "seed: " << seed << std::endl;
     srand(seed);

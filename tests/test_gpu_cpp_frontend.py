@@ -22,7 +22,7 @@ def test_cpp_front_end(built, name, parts):
     r = subprocess.run([str(exe), "12345"], capture_output=True, text=True, env=env, timeout=300)
     print(r.stdout[-3000:])
     print(r.stderr[-3000:])
-    assert r.returncode == 0, f"{name} failed:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
+    assert r.returncode == 0, f"{name} exited with status {r.returncode}:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
     assert " 0 failures" in r.stdout
 
 
@@ -44,7 +44,7 @@ def _run_binary(name: str, parts: str, timeout: int):
                        timeout=timeout)
     print(r.stdout[-3000:])
     print(r.stderr[-3000:])
-    assert r.returncode == 0 and " 0 failures" in r.stdout, f"{name} failed:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
+    assert r.returncode == 0 and " 0 failures" in r.stdout, f"{name} exited with status {r.returncode}:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
 
 
 def test_cpp_stencil_single_slice(built):

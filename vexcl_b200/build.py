@@ -91,7 +91,7 @@ def build_cpp_tests(force: bool = False):
         out = bin_dir / cpp.stem
         outs.append(out)
         if force or _stale(out, [cpp, *headers, LIB]):
-            _run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused-function", "-I", ROOT / "include", cpp, "-o", out,
+            _run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused-function", "-rdynamic", "-I", ROOT / "include", cpp, "-o", out,
                   "-L", LIB.parent, "-lvexb200", f"-Wl,-rpath,{LIB.parent}", "-Wl,-rpath,$ORIGIN/../../../vexcl_b200",
                   "-lpthread", "-ldl"])
     return outs

@@ -332,6 +332,7 @@ int vexb::ccsr_create_ex(int dev, size_t n, size_t xlen, size_t m, const void *i
 
 extern "C" int vexb_ccsr_destroy(vexb_ccsr *A) {
     if (!A) return VEXB_OK;
+    VEXB_RELEASE_GUARD();
     DeviceGuard g(A->dev);
     cudaFree(A->idx); cudaFree(A->row); cudaFree(A->col); cudaFree(A->val);
     delete A;

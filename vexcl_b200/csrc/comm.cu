@@ -84,6 +84,7 @@ extern "C" int vexb_comm_create_all(int ndev, const int *devs, vexb_comm **comms
 
 extern "C" int vexb_comm_destroy(vexb_comm *comm) {
     if (!comm) return VEXB_OK;
+    VEXB_RELEASE_GUARD();
     if (comm->comm && g_nccl.handle) { DeviceGuard g(comm->dev); g_nccl.ncclCommDestroy(comm->comm); }
     delete comm;
     return VEXB_OK;

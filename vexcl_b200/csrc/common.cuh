@@ -27,6 +27,14 @@ struct DeviceGuard {
 
 int sm_count(int dev);
 
+// Teardown at process exit.  The CUDA runtime registers its own exit handler at the first API call; a host program that
+// keeps its vex::Context in a static (the reference's test fixture does) destroys queues, buffers and matrices AFTER that
+// handler has run, and CUDA calls on a runtime that is being unloaded crash now and then.  note_cuda_started() registers
+// an exit handler right after the first CUDA call -- it therefore runs BEFORE the runtime's -- and from then on every
+// release entry point returns at once (the process is going away; the driver reclaims the memory).
+void note_cuda_started();
+bool process_exiting();
+
 inline size_t dtype_size(int dt) {
     switch (dt) {
         case VEXB_F64: case VEXB_I64: case VEXB_U64: return 8;
@@ -44,6 +52,8 @@ inline size_t dtype_size(int dt) {
     return VEXB_ERR_CUDA; } } while (0)
 
 #define VEXB_CHECK(cond, ...) do { if (!(cond)) VEXB_FAIL(VEXB_ERR_INVALID, __VA_ARGS__); } while (0)
+
+#define VEXB_RELEASE_GUARD() do { if (::vexb::process_exiting()) return VEXB_OK; } while (0)
 
 #define VEXB_TRY(expr) do { int s_ = (expr); if (s_ != VEXB_OK) return s_; } while (0)
 

@@ -36,6 +36,7 @@ using namespace vexb;
 
 extern "C" int vexb_dspmat_destroy(vexb_dspmat *A) {
     if (!A) return VEXB_OK;
+    VEXB_RELEASE_GUARD();
     DeviceGuard g(A->dev);
     vexb_spmat_destroy(A->loc); vexb_spmat_destroy(A->bnd); vexb_spmat_destroy(A->rem);
     cudaFree(A->send_cols); cudaFree(A->send_buf); cudaFree(A->ghost_buf);

@@ -41,6 +41,7 @@ extern "C" int vexb_graph_launch(vexb_graph *graph, void *stream) {
 
 extern "C" int vexb_graph_destroy(vexb_graph *graph) {
     if (!graph) return VEXB_OK;
+    VEXB_RELEASE_GUARD();
     DeviceGuard g(graph->dev);
     if (graph->exec) cudaGraphExecDestroy(graph->exec);
     if (graph->graph) cudaGraphDestroy(graph->graph);

@@ -122,6 +122,7 @@ extern "C" int vexb_peer_create_all(int ndev, const int *devs, vexb_peer **peers
 
 extern "C" int vexb_peer_destroy(vexb_peer *peer) {
     if (!peer) return VEXB_OK;
+    VEXB_RELEASE_GUARD();
     DeviceGuard g(peer->dev);
     for (int p = 0; p < peer->nranks; ++p) if (peer->ipc_opened[p]) cudaIpcCloseMemHandle(peer->peers[p]);
     cudaFree(peer->mailbox);

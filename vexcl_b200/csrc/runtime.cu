@@ -40,6 +40,14 @@ int sm_count(int dev) {
     return n;
 }
 
+static std::atomic<bool> g_exiting{false};
+static void mark_exiting() { g_exiting.store(true); }
+bool process_exiting() { return g_exiting.load(std::memory_order_relaxed); }
+void note_cuda_started() {
+    static std::once_flag once;
+    std::call_once(once, [] { atexit(mark_exiting); });
+}
+
 } // namespace vexb
 
 using namespace vexb;
@@ -54,6 +62,7 @@ int vexb_init(void) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) VEXB_FAIL(VEXB_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
     if (n <= 0) VEXB_FAIL(VEXB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    note_cuda_started();
     return VEXB_OK;
 }
 
@@ -63,6 +72,7 @@ int vexb_device_count(int *n) {
     VEXB_CHECK(n, "n is NULL");
     cudaError_t e = cudaGetDeviceCount(n);
     if (e != cudaSuccess) { *n = 0; VEXB_FAIL(VEXB_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e)); }
+    note_cuda_started();
     return VEXB_OK;
 }
 
@@ -105,9 +115,11 @@ int vexb_stream_create(int dev, void **stream) {
     VEXB_CHECK(stream, "stream is NULL");
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     cudaStream_t s; VEXB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    note_cuda_started();
     *stream = (void *)s; return VEXB_OK;
 }
 int vexb_stream_destroy(int dev, void *stream) {
+    VEXB_RELEASE_GUARD();
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     VEXB_CUDA(cudaStreamDestroy((cudaStream_t)stream)); return VEXB_OK;
 }
@@ -126,6 +138,7 @@ int vexb_event_create(int dev, void **event) {
     *event = (void *)e; return VEXB_OK;
 }
 int vexb_event_destroy(int dev, void *event) {
+    VEXB_RELEASE_GUARD();
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     VEXB_CUDA(cudaEventDestroy((cudaEvent_t)event)); return VEXB_OK;
 }
@@ -155,10 +168,12 @@ int vexb_malloc(int dev, size_t bytes, void **p) {
     cudaError_t e = cudaMalloc(p, bytes);
     if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); VEXB_FAIL(VEXB_ERR_NOMEM, "cudaMalloc(%zu) out of memory", bytes); }
     VEXB_CUDA(e);
+    note_cuda_started();
     return VEXB_OK;
 }
 int vexb_free(int dev, void *p) {
     if (!p) return VEXB_OK;
+    VEXB_RELEASE_GUARD();
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
     VEXB_CUDA(cudaFree(p)); return VEXB_OK;
 }
@@ -166,7 +181,7 @@ int vexb_host_alloc(size_t bytes, void **p) {
     VEXB_CHECK(p, "p is NULL");
     VEXB_CUDA(cudaMallocHost(p, bytes ? bytes : 1)); return VEXB_OK;
 }
-int vexb_host_free(void *p) { if (p) VEXB_CUDA(cudaFreeHost(p)); return VEXB_OK; }
+int vexb_host_free(void *p) { VEXB_RELEASE_GUARD(); if (p) VEXB_CUDA(cudaFreeHost(p)); return VEXB_OK; }
 
 int vexb_h2d(int dev, void *dst, const void *src, size_t bytes, void *stream, int blocking) {
     if (!bytes) return VEXB_OK;

@@ -951,6 +951,7 @@ extern "C" int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols
 
 extern "C" int vexb_spmat_destroy(vexb_spmat *A) {
     if (!A) return VEXB_OK;
+    VEXB_RELEASE_GUARD();
     DeviceGuard g(A->dev);
     cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile); cudaFree(A->wtile); cudaFree(A->d_desc);
     vexb_ccsr_destroy(A->patterns);
