@@ -240,6 +240,10 @@ int vexb_jit_source(int lhs_dtype, int assign_op, const vexb_expr *expr, char *b
  * "eval.jit": 0 = interpreter only, 1 = compile synchronously, 2 = this, the default).  *pending = 1 while any such
  * compilation is still running: benchmarks and tests wait on it to time / check the specialised kernel. */
 int vexb_jit_pending(int *pending);
+/* Compile the kernel of a request shape before its first use (background != 0: on a background thread, as the first
+ * vexb_eval of a new shape does in the default mode).  Needs NVRTC, no device.  A process may exit while background
+ * compilations run: the thread that started them waits for the one in flight and cancels the rest on its way out. */
+int vexb_jit_precompile(int lhs_dtype, int assign_op, const vexb_expr *expr, int background);
 /* Which kernel vexb_eval would take for this request: writes a short
  * name ("sweep:muladd", "interp", "jit", ...) to buf. */
 int vexb_eval_path(int lhs_dtype, int assign_op, const vexb_expr *expr, char *buf, size_t buflen);

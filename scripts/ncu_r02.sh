@@ -9,6 +9,7 @@ mkdir -p gpurun_out /tmp/ncu
 NCU="ncu --clock-control none"
 want() { [ $# -eq 0 ] || return 0; }
 TARGETS="${*:-launches hell csr_scalar csr_warp ccsr ccsr_jit stencil dist_apply cg_update interp hell_multi}"
+KEEP_REP="${KEEP_REP:-csr_warp stencil ccsr_jit}"
 has() { case " $TARGETS " in *" $1 "*) return 0;; esac; return 1; }
 if has launches; then
     timeout 500 $NCU --metrics gpu__time_duration.sum -c 1500 --csv --log-file gpurun_out/r02_launches_bench.csv \
@@ -23,9 +24,12 @@ cap() {  # name regex count targets...
     local rc=$?
     ncu -i /tmp/ncu/r02_ncu_$name.ncu-rep --page raw --csv > gpurun_out/r02_ncu_${name}_raw.csv 2>/dev/null
     ncu -i /tmp/ncu/r02_ncu_$name.ncu-rep --page source --csv --print-source sass > gpurun_out/r02_ncu_${name}_sass.csv 2>/dev/null
+    gzip -f gpurun_out/r02_ncu_${name}_sass.csv
     local sz=$(stat -c %s /tmp/ncu/r02_ncu_$name.ncu-rep 2>/dev/null || echo 0)
-    [ "$sz" -gt 0 ] && [ "$sz" -lt 9000000 ] && cp /tmp/ncu/r02_ncu_$name.ncu-rep gpurun_out/
-    echo "$name rc=$rc rep=$sz raw=$(stat -c %s gpurun_out/r02_ncu_${name}_raw.csv) sass=$(stat -c %s gpurun_out/r02_ncu_${name}_sass.csv)"
+    # gpurun_out/ comes back only if it stays under 64 MiB: keep a report only while the directory is under 30 MB
+    local used=$(du -sm gpurun_out | cut -f1)
+    case " $KEEP_REP " in *" $name "*) [ "$sz" -gt 0 ] && [ "$sz" -lt 9000000 ] && [ "$used" -lt 30 ] && cp /tmp/ncu/r02_ncu_$name.ncu-rep gpurun_out/;; esac
+    echo "$name rc=$rc rep=$sz raw=$(stat -c %s gpurun_out/r02_ncu_${name}_raw.csv) sass.gz=$(stat -c %s gpurun_out/r02_ncu_${name}_sass.csv.gz)"
 }
 cap hell '^hell_kernel' 2 hell
 cap csr_scalar 'csr_scalar_kernel' 2 csr_poisson
@@ -37,4 +41,5 @@ cap dist_apply 'dist_apply_kernel' 1 cg
 cap cg_update 'cg_update' 2 cg
 cap interp '^interp_kernel' 1 vec
 cap hell_multi 'hell_multi_kernel' 2 hell multi_rhs
+if [ "$(du -sm gpurun_out | cut -f1)" -ge 60 ]; then rm -f gpurun_out/*.ncu-rep; echo "reports dropped to stay under the size limit"; fi
 du -sh gpurun_out

@@ -27,6 +27,8 @@ KEYS = {
     "launch__occupancy_limit_shared_mem": "lim_smem",
     "launch__occupancy_limit_warps": "lim_warps",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pct",
+    "lts__t_sector_hit_rate.pct": "l2_hit",
+    "l1tex__t_sector_hit_rate.pct": "l1_hit",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "lsu_pct",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "smem_wavefronts",
     "smsp__cycles_active.avg": "smsp_cycles",
@@ -46,11 +48,14 @@ def to_us(v, unit):
 
 def main():
     for path in sys.argv[1:]:
-        r = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True)
-        if r.returncode != 0:
-            print(f"## {path}\n\ncannot read: {r.stderr[:300]}\n")
-            continue
-        rows = list(csv.reader(io.StringIO(r.stdout)))
+        if path.endswith(".csv"):                              # already exported with `ncu -i rep --page raw --csv`
+            rows = list(csv.reader(open(path)))
+        else:
+            r = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True)
+            if r.returncode != 0:
+                print(f"## {path}\n\ncannot read: {r.stderr[:300]}\n")
+                continue
+            rows = list(csv.reader(io.StringIO(r.stdout)))
         hdr, units = rows[0], rows[1]
         ix = {h: i for i, h in enumerate(hdr)}
         print(f"## {Path(path).name}\n")
@@ -69,8 +74,7 @@ def main():
             wr = to_bytes(*vals["dram_wr"]) if "dram_wr" in vals else 0.0
             stalls = []
             for h in hdr:
-                if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") or \
-                   h.startswith("smsp__average_warp_latency_issue_stalled_") or h.startswith("smsp__average_warps_issue_stalled_"):
+                if h.startswith("smsp__average_warp") and "stalled_" in h and h.endswith(".ratio"):
                     try:
                         stalls.append((float(row[ix[h]].replace(",", "")), h.split("stalled_")[1].split("_per_")[0].replace(".ratio", "")))
                     except (ValueError, IndexError):
@@ -79,7 +83,7 @@ def main():
             f = lambda k, fmt="{:.1f}": fmt.format(vals[k][0]) if k in vals else "-"
             print(f"* `{name}` grid {f('grid', '{:.0f}')} x {f('block', '{:.0f}')}, {f('regs', '{:.0f}')} regs: **{t_us:.1f} us**, "
                   f"DRAM {rd / 1e6:.1f} + {wr / 1e6:.1f} MB = {(rd + wr) / 1e6:.1f} MB ({(rd + wr) / t_us / 1e3 if t_us == t_us else 0:.0f} GB/s, {f('dram_pct')} % of peak); "
-                  f"L2 {f('l2_pct')} %, L1 {f('l1_pct')} %, issue {f('issue_pct')} %, FP64 pipe {f('fp64_pct')} %, LSU {f('lsu_pct')} %, "
+                  f"L2 {f('l2_pct')} % (hit {f('l2_hit')} %), L1 {f('l1_pct')} % (hit {f('l1_hit')} %), issue {f('issue_pct')} %, FP64 pipe {f('fp64_pct')} %, LSU {f('lsu_pct')} %, "
                   f"warps active {f('occ_pct')} % (limits: regs {f('lim_regs', '{:.0f}')}, smem {f('lim_smem', '{:.0f}')}, warps {f('lim_warps', '{:.0f}')} blocks/SM); "
                   f"top stalls: " + ", ".join(f"{n} {v:.2f}" for v, n in stalls[:5]))
         print()

@@ -1,0 +1,150 @@
+"""Round-2 timing probe (one GPU, CUDA events): the kernels changed since the last bench line.
+    python scripts/probe_r02.py > gpurun_out/r02_probe.json"""
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import vexcl_b200 as vx
+from vexcl_b200 import gen, _lib as L
+from vexcl_b200.api import Event
+
+ctx = vx.Context([0])
+PEAK = 6584.5
+out = {}
+
+
+def timeit(fn, steps=30, warm=5):
+    for _ in range(warm):
+        fn()
+    ctx.finish()
+    e0, e1 = Event(ctx), Event(ctx)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record(); e1.sync()
+    return e0.elapsed_ms(e1) / steps
+
+
+what = sys.argv[1:] or ["ring", "multi", "ccsr", "p3d", "cg", "stencil"]
+
+if "ring" in what:
+    for label, (row, col, val) in (("irregular 4M U[0,32) gaps U[1,64)", gen.irregular_rows(4_000_000, 0, 32, seed=1)),
+                                   ("poisson2d 3162^2", gen.poisson_strip(2, 3162))):
+        n = row.size - 1
+        nb = gen.spmv_bytes(n, n, int(row[-1]))
+        x, y, y4 = vx.vector(ctx, n), vx.vector(ctx, n), vx.vector(ctx, n)
+        x.assign(vx.ElementIndex() * (1.0 / n) + 0.5)
+        A = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_CSR)
+        res = {}
+        vx.set_param("spmv.kernel", 4)
+        A.apply(x, y4, 1.0, False)
+        ref = y4.read()
+        for k in (3, 4):
+            vx.set_param("spmv.kernel", k)
+            ms = timeit(lambda: A.apply(x, y, 1.0, False))
+            res[f"kernel={k}"] = {"ms": ms, "frac": nb / ms / 1e6 / PEAK}
+        vx.set_param("spmv.kernel", 5)
+        for warps in (8, 4):
+            for stages in (2, 3, 4):
+                for ctas in (0, 1, 2, 3, 4):
+                    vx.set_param("spmv.ring_warps", warps); vx.set_param("spmv.ring_stages", stages); vx.set_param("spmv.ctas_per_sm", ctas)
+                    try:
+                        y.assign(0.0)
+                        A.apply(x, y, 1.0, False)
+                        same = bool(np.array_equal(y.read(), ref))
+                        ms = timeit(lambda: A.apply(x, y, 1.0, False))
+                        res[f"kernel=5 warps={warps} stages={stages} ctas_per_sm={ctas}"] = {"ms": ms, "frac": nb / ms / 1e6 / PEAK, "same_bits_as_warp_tiles": same}
+                    except vx.VexbError as e:
+                        res[f"kernel=5 warps={warps} stages={stages} ctas_per_sm={ctas}"] = {"error": str(e)[:200]}
+        vx.set_param("spmv.ctas_per_sm", 0); vx.set_param("spmv.kernel", -1)
+        out[label] = res
+        del A, x, y, y4
+
+if "multi" in what or "p3d" in what:
+    pass
+
+if "multi" in what:
+    row, col, val = gen.poisson_strip(2, 3162)
+    N = row.size - 1
+    A = vx.SpMat(ctx, N, N, row, col, val, vx.FMT_AUTO)
+    xs = [vx.vector(ctx, N) for _ in range(4)]
+    ys = [vx.vector(ctx, N) for _ in range(4)]
+    for r, v in enumerate(xs):
+        v.assign(vx.ElementIndex() * (1.0 / N) + 0.25 * r)
+    one = timeit(lambda: A.apply(xs[0], ys[0], 1.0, False))
+    res = {"ms_one": one}
+    for fl in (0, 1, 2, 3):
+        vx.set_param("spmv.multi_flags", fl)
+        four = timeit(lambda: A.apply_multi(xs, ys, 1.0, False))
+        res[f"flags={fl}"] = {"ms_four": four, "ratio": four / one}
+    vx.set_param("spmv.multi_flags", 0)
+    out["multi_rhs"] = res
+    del A, xs, ys
+
+if "p3d" in what:
+    row, col, val = gen.poisson_strip(3, 256)
+    N = row.size - 1
+    nb = gen.spmv_bytes(N, N, int(row[-1]))
+    x, y = vx.vector(ctx, N), vx.vector(ctx, N)
+    x.assign(vx.ElementIndex() * (1.0 / N) + 0.5)
+    res = {}
+    for c16 in (0, 1):
+        vx.set_param("spmv.col16", c16)
+        A = vx.SpMat(ctx, N, N, row, col, val, vx.FMT_AUTO)
+        ms = timeit(lambda: A.apply(x, y, 1.0, False))
+        info = A.info().loc
+        res[f"col16={c16}"] = {"ms": ms, "gbs_canonical": nb / ms / 1e6, "device_bytes": int(info.device_bytes), "ell_width": int(info.ell_width)}
+        del A
+    vx.set_param("spmv.col16", 1)
+    out["poisson3d 256^3 hell"] = res
+    del x, y
+
+if "ccsr" in what:
+    n = 256
+    N = n ** 3
+    idx, row, col, val = gen.poisson_ccsr(n)
+    x, y = vx.vector(ctx, N), vx.vector(ctx, N)
+    x.assign(vx.ElementIndex() * (1.0 / N) + 0.5)
+    y.assign(0.0)
+    res = {}
+    for jit in (0, 1):
+        vx.set_param("ccsr.jit", jit)
+        A = vx.SpMatCCSR(ctx, N, idx, row, col, val)
+        for app in (True, False):
+            ms = timeit(lambda: A.apply(x, y, 1.0, app))
+            comp = N * (1 + 16 + (8 if app else 0))
+            res[f"jit={jit} append={app}"] = {"ms": ms, "gbs_compulsory": comp / ms / 1e6, "frac": comp / ms / 1e6 / PEAK}
+        del A
+    vx.set_param("ccsr.jit", 1)
+    out["ccsr 256^3"] = res
+    del x, y
+
+if "cg" in what:
+    from vexcl_b200.solvers import CGFused
+    n = 256
+    N = n ** 3
+    row, col, val = gen.poisson_strip(3, n, spd=True)
+    A = vx.SpMat(ctx, N, N, row, col, val)
+    b, x = vx.vector(ctx, N), vx.vector(ctx, N)
+    b.assign(((vx.ElementIndex() * 2654435761) % 1000003) * (1.0 / 1000003) - 0.5)
+    x.assign(0.0)
+    cg = CGFused(A, b, x)
+    cg.capture()
+    ms = timeit(lambda: cg.run(1), steps=40)
+    out["cg fused 256^3 graph"] = {"ms_per_iteration": ms, "residual2": cg.residual2()}
+    del cg, A, b, x
+
+if "stencil" in what:
+    n, width = 1 << 26, 21
+    S = vx.stencil(ctx, np.full(width, 1.0 / width), width // 2)
+    a, b = vx.vector(ctx, n), vx.vector(ctx, n)
+    a.assign(vx.ElementIndex() * (1.0 / n) + 0.5)
+    ms = timeit(lambda: S.apply(a, b, 1.0, False))
+    out["stencil 2^26 w21"] = {"ms": ms, "gbs_compulsory": 16 * n / ms / 1e6, "frac": 16 * n / ms / 1e6 / PEAK}
+
+print(json.dumps(out, indent=1))

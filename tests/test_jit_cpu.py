@@ -52,7 +52,8 @@ def test_user_function_source_and_nvrtc_compile(env):
     # compound assignment and mixed types go through the same printer
     i = fake_vec(1024, np.int32, 0x9000)
     src = jit_source(api, L, i, L.ADD, greater(x, 0.5) + (i << 2))
-    assert "lhs[i] = (int)((int)lhs[i] + (int)" in src and "NVRTC: ok" in src
+    assert "return (int)((int)lhs[i] + (int)" in src and "NVRTC: ok" in src
+    assert "a3 = vexb_elem(tt, lhs, i + 3 * stride, off)" in src           # four elements per thread in flight
     # every operator family compiles
     f = fake_vec(1024, np.float32, 0xa000)
     e = vx.if_else(x > y, vx.sin(x) * vx.pow_(y, 2.0), vx.fmin(x, y)) + vx.fma(x, y, z) - vx.fabs(-x) + f * i + vx.ElementIndex(3) % 7
@@ -93,10 +94,13 @@ def test_ccsr_specialised_kernel_source_compiles(env):
     idx, row, col, val = gen.poisson_ccsr(32)
     src = _ccsr_source(L, row, col, val)
     assert "NVRTC: ok" in src and "vexb_ccsr_jit" in src and "const unsigned char *__restrict__ idx" in src
-    assert src.count("case ") == 2 and src.count("__ldg(") == 8
-    assert "__ldg(xi + (-1024))" in src and "__ldg(xi + (1024))" in src                   # +-n^2 as address immediates
+    # 4 rows per thread (rows of <= 8 entries): one straight-line path for threads whose rows share a unique row, one
+    # switch per row otherwise -> every unique row appears 1 + 4 times as a case, its gathers 4 + 4 times
+    assert "4 rows per thread" in src and src.count("case ") == 2 * 5 and src.count("__ldg(") == 8 * 8
+    assert "__ldg(xi0 + (-1024))" in src and "__ldg(xi3 + (1024))" in src                 # +-n^2 as address immediates
     assert float.fromhex(src.split("__dmul_rn(")[1].split(",")[0]) == 1.0                  # boundary row: 1 * x[i]
-    lits = [float.fromhex(t.split(",")[0]) for t in src.split("__dmul_rn(")[1:9]]
+    slow = src.split("} else {")[1]                                                        # the per-row switches: row 0 first
+    lits = [float.fromhex(t.split(",")[0]) for t in slow.split("__dmul_rn(")[1:9]]
     assert lits == list(val)                                                                # values survive exactly (hex literals)
     # single precision, 2-byte idx, a row longer than one gather group, an empty row
     rng = np.random.default_rng(2)
@@ -105,7 +109,9 @@ def test_ccsr_specialised_kernel_source_compiles(env):
     valf = rng.random(14).astype(np.float32)
     src = _ccsr_source(L, row, col, valf, idx_bytes=2)
     assert "NVRTC: ok" in src and "const unsigned short *__restrict__ idx" in src and "__fmul_rn(" in src
-    assert [np.float32(float.fromhex(t.split("f,")[0])) for t in src.split("__fmul_rn(")[1:15]] == list(valf)
+    assert "2 rows per thread" in src
+    slow = src.split("} else {")[1]
+    assert [np.float32(float.fromhex(t.split("f,")[0])) for t in slow.split("__fmul_rn(")[1:15]] == list(valf)
     with pytest.raises(vx.VexbError, match="too large"):
         _ccsr_source(L, np.arange(41), np.zeros(40, np.int32), np.ones(40), compile=False)
 
@@ -156,13 +162,13 @@ def test_compound_shifts_keep_the_type_of_the_left_operand(env):
     vx, api, L, fake_vec = env
     a, b = fake_vec(64, np.int32, 0x1000), fake_vec(64, np.uint32, 0x2000)
     src = jit_source(api, L, a, L.RSH, b)
-    assert "lhs[i] = (int)((int)lhs[i] >> (int)" in src and "NVRTC: ok" in src
+    assert "return (int)((int)lhs[i] >> (int)" in src and "NVRTC: ok" in src
     w = fake_vec(64, np.uint64, 0x3000)
     src = jit_source(api, L, a, L.LSH, w)
-    assert "lhs[i] = (int)((int)lhs[i] << (int)" in src
+    assert "return (int)((int)lhs[i] << (int)" in src
     # other compound operators still use the common type
     src = jit_source(api, L, a, L.ADD, b)
-    assert "lhs[i] = (int)((unsigned int)lhs[i] + (unsigned int)" in src
+    assert "return (int)((unsigned int)lhs[i] + (unsigned int)" in src
 
 
 def test_sixteen_terminals_with_converted_scalars_normalise(env):
@@ -181,3 +187,45 @@ def test_sixteen_terminals_with_converted_scalars_normalise(env):
     i = fake_vec(256, np.int32, 0x30000)
     src = jit_source(api, L, z, L.SET, (vs[0] * s) + (i * s), compile=False)
     assert "vexb_jit_kernel" in src
+
+
+def test_process_may_exit_while_background_compilations_run(built):
+    """A host program that leaves main() while NVRTC is compiling on a background thread must exit cleanly (NVRTC's own
+    lazily registered exit handlers used to run first and pull its statics from under the compilation: SIGSEGV on every
+    cold start of tests/cpp/test_vector_arithmetics, profiles/r02_exit_crash.md)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    code = r"""
+import ctypes as C, sys
+import numpy as np
+sys.path.insert(0, %r)
+import vexcl_b200 as vx
+from vexcl_b200 import api, _lib as L
+class FakeCtx:
+    nparts, local, is_distributed = 1, [0], False
+    def partition(self, n): return vx.partition(n, 1)
+def fake_vec(n, dt, addr):
+    v = api.vector.__new__(api.vector)
+    v.ctx, v.n, v.np_dtype, v.dtype, v.part, v.bufs = FakeCtx(), n, np.dtype(dt), api._vdt(dt), vx.partition(n, 1), {0: C.c_void_p(addr)}
+    return v
+x, y, z = (fake_vec(1024, np.float64, 0x1000 * (k + 1)) for k in range(3))
+def lowered(expr):
+    low = api._Lowering(0, 0); low.size = 1024; low.lower(api.wrap(expr)); return low
+first = lowered(x * y + z)
+L.check(L.lib().vexb_jit_precompile(z.dtype, L.SET, C.byref(first.e), 1))      # the first compilation is a background one, as in a real run:
+pend = C.c_int(1)                                                                # our atexit handler is registered BEFORE NVRTC's own
+while pend.value:
+    L.check(L.lib().vexb_jit_pending(C.byref(pend)))
+for k, e in enumerate((vx.sin(x) * y + z / 3.0, (x - y) * (x + y) / z, vx.sqrt(x) + vx.cos(y) * z, x / y / z + 1.0)):
+    low = lowered(e)
+    L.check(L.lib().vexb_jit_precompile(z.dtype, L.SET, C.byref(low.e), 1))    # background, as the first use of a new shape
+pend = C.c_int(0); L.check(L.lib().vexb_jit_pending(C.byref(pend)))
+print("pending", pend.value, flush=True)
+sys.exit(0)                                                                      # leave while they compile
+""" % str(root)
+    for _ in range(3):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, f"exit status {r.returncode}\n{r.stdout[-500:]}\n{r.stderr[-1500:]}"
+        assert "pending 1" in r.stdout                                                # the exit really overlapped a compilation

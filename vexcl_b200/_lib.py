@@ -178,6 +178,7 @@ def lib():
         "vexb_spmv_multi": ([i, vp, vp, i, P(vp), P(vp), d, i], i),
         "vexb_dspmat_apply_multi": ([i, P(vp), P(vp), P(vp), i, P(vp), P(vp), d, i], i),
         "vexb_jit_pending": ([P(i)], i),
+        "vexb_jit_precompile": ([i, i, P(Expr), i], i),
         "vexb_reduce_multi": ([i, vp, P(Expr), i, sz, sz, i, P(i), vp, vp, vp], i),
         "vexb_cg_update_r": ([i, vp, i, sz, vp, vp, vp, vp, vp, vp, vp], i),
         "vexb_cg_update_xp": ([i, vp, i, sz, vp, vp, vp, vp, vp, vp], i),

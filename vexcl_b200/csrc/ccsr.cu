@@ -40,7 +40,7 @@ template <> __device__ __forceinline__ float c_add<float>(float a, float b) { re
 
 constexpr size_t CCSR_SMEM_LIMIT = 40 * 1024;
 constexpr long CCSR_DEFAULT_KERNEL = 1;
-constexpr long CCSR_DEFAULT_JIT = 0;        // round 1: the specialised kernel compiles (tests/test_jit_cpu.py) but has not run on a GPU yet
+constexpr long CCSR_DEFAULT_JIT = 1;        // the matrix-specialised NVRTC kernel (same bits; the table kernel serves when NVRTC is missing or the table is large)
 
 template <class T, class I, bool SMEM, int CCSR_THREADS, int CCSR_BATCH, bool HOIST>
 __global__ void __launch_bounds__(CCSR_THREADS) ccsr_kernel(size_t n, int m, int nnz, const I *__restrict__ idx,
@@ -191,43 +191,100 @@ static int launch(const vexb_ccsr *A, cudaStream_t st, const T *x, T *y, T alpha
 // separate, storage order), so the bits are identical.  Eligible when the table is small (CCSR_JIT_MAX_*).
 constexpr size_t CCSR_JIT_MAX_ROWS = 32, CCSR_JIT_MAX_NNZ = 256;
 
+// Rows per thread of the generated kernel: the product is two dependent memory round trips per row (idx[i], then the
+// gathers); at one row per thread the kernel is bound by exactly that latency (ncu: 36 of 41 cycles between issues on
+// long_scoreboard, DRAM at 47 %).  With R rows per thread the R idx bytes travel together, and when the R rows share a
+// unique row (the rule on structured grids) all R * width gathers are in flight at once.
+static int ccsr_jit_rows_per_thread(const std::vector<int> &row) {
+    int maxw = 0;
+    for (size_t u = 0; u + 1 < row.size(); ++u) maxw = std::max(maxw, row[u + 1] - row[u]);
+    return maxw <= 8 ? 4 : maxw <= 16 ? 2 : 1;
+}
+
 static std::string ccsr_jit_source(int val_dtype, int idx_bytes, const std::vector<int> &row, const std::vector<int> &col,
                                    const std::vector<double> &val) {
     const bool f64 = val_dtype == VEXB_F64;
     const char *T = f64 ? "double" : "float";
     const char *I = idx_bytes == 1 ? "unsigned char" : idx_bytes == 2 ? "unsigned short" : "int";
     const char *mul = f64 ? "__dmul_rn" : "__fmul_rn", *add = f64 ? "__dadd_rn" : "__fadd_rn";
+    const int R = ccsr_jit_rows_per_thread(row);
+    const int minblocks = R == 4 ? 3 : R == 2 ? 4 : 8;
     std::string s;
     char buf[512];
-    s += "// generated by libvexb200 (csrc/ccsr.cu) for one CCSR matrix: " + std::to_string(row.size() - 1) + " unique rows, " +
-         std::to_string(col.size()) + " entries\n";
-    snprintf(buf, sizeof(buf), "extern \"C\" __global__ void __launch_bounds__(256) vexb_ccsr_jit(unsigned long long n, const %s *__restrict__ idx,\n"
-                               "        const %s *__restrict__ x, %s *y, %s alpha, int append) {\n", I, T, T, T);
-    s += buf;
-    s += "    const unsigned long long i = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;\n"
-         "    if (i >= n) return;\n"
-         "    const int u = (int)idx[i];\n";
-    s += std::string("    ") + T + " yo = 0;\n    if (append) yo = y[i];\n";
-    s += std::string("    const ") + T + " *xi = x + i;\n    " + T + " sum = 0;\n    switch (u) {\n";
-    for (size_t u = 0; u + 1 < row.size(); ++u) {
-        s += "    case " + std::to_string(u) + ": {\n";
-        for (int base = row[u]; base < row[u + 1]; base += 8) {              // gathers in groups of 8, then the products in order
+    auto lit = [&](double v) { if (f64) snprintf(buf, sizeof(buf), "%a", v); else snprintf(buf, sizeof(buf), "%af", (double)(float)v); return std::string(buf); };
+    // products of unique row u for the row whose variables carry the suffix k: gathers in groups of 8, then the products in order
+    auto row_body = [&](size_t u, int k, const char *indent) {
+        std::string r;
+        for (int base = row[u]; base < row[u + 1]; base += 8) {
             const int end = std::min(base + 8, row[u + 1]);
             for (int j = base; j < end; ++j) {
-                snprintf(buf, sizeof(buf), "        const %s x%d = __ldg(xi + (%d));\n", T, j - row[u], col[j]);
-                s += buf;
+                snprintf(buf, sizeof(buf), "%sconst %s x%d_%d = __ldg(xi%d + (%d));\n", indent, T, k, j - row[u], k, col[j]);
+                r += buf;
             }
             for (int j = base; j < end; ++j) {
-                if (f64) snprintf(buf, sizeof(buf), "        sum = %s(sum, %s(%a, x%d));\n", add, mul, val[j], j - row[u]);
-                else snprintf(buf, sizeof(buf), "        sum = %s(sum, %s(%af, x%d));\n", add, mul, (double)(float)val[j], j - row[u]);
-                s += buf;
+                const std::string v = lit(val[j]);
+                snprintf(buf, sizeof(buf), "%ssum%d = %s(sum%d, %s(%s, x%d_%d));\n", indent, k, add, k, mul, v.c_str(), k, j - row[u]);
+                r += buf;
             }
         }
-        s += "    } break;\n";
+        return r;
+    };
+    s += "// generated by libvexb200 (csrc/ccsr.cu) for one CCSR matrix: " + std::to_string(row.size() - 1) + " unique rows, " +
+         std::to_string(col.size()) + " entries, " + std::to_string(R) + " rows per thread\n";
+    snprintf(buf, sizeof(buf), "extern \"C\" __global__ void __launch_bounds__(256, %d) vexb_ccsr_jit(unsigned long long n, const %s *__restrict__ idx,\n"
+                               "        const %s *__restrict__ x, %s *y, %s alpha, int append) {\n", minblocks, I, T, T, T);
+    s += buf;
+    snprintf(buf, sizeof(buf), "    const unsigned long long ib = (unsigned long long)blockIdx.x * %dull + threadIdx.x;\n    if (ib >= n) return;\n", 256 * R);
+    s += buf;
+    for (int k = 0; k < R; ++k) {
+        snprintf(buf, sizeof(buf), "    const unsigned long long i%d = ib + %dull; const bool in%d = i%d < n;\n", k, 256 * k, k, k);
+        s += buf;
     }
-    s += "    default: break;\n    }\n";
-    s += std::string("    const ") + T + " v = " + mul + "(alpha, sum);\n";
-    s += std::string("    y[i] = append ? ") + add + "(yo, v) : v;\n}\n";
+    for (int k = 0; k < R; ++k) { snprintf(buf, sizeof(buf), "    const int u%d = in%d ? (int)idx[i%d] : -1;\n", k, k, k); s += buf; }
+    for (int k = 0; k < R; ++k) { snprintf(buf, sizeof(buf), "    %s yo%d = 0; if (append && in%d) yo%d = y[i%d];\n", T, k, k, k, k); s += buf; }
+    for (int k = 0; k < R; ++k) { snprintf(buf, sizeof(buf), "    const %s *xi%d = x + i%d; %s sum%d = 0;\n", T, k, k, T, k); s += buf; }
+    if (R > 1) {
+        // fast path: the thread's rows share one unique row -> straight-line code, every gather issued before the first product
+        s += "    if (";
+        for (int k = 1; k < R; ++k) { snprintf(buf, sizeof(buf), "%su0 == u%d", k > 1 ? " && " : "", k); s += buf; }
+        s += ") {\n        switch (u0) {\n";
+        for (size_t u = 0; u + 1 < row.size(); ++u) {
+            s += "        case " + std::to_string(u) + ": {\n";
+            const int w = row[u + 1] - row[u];
+            if (w <= 8) {
+                // all R * w gathers, then the products row by row (each row's sum in storage order)
+                for (int k = 0; k < R; ++k)
+                    for (int j = row[u]; j < row[u + 1]; ++j) {
+                        snprintf(buf, sizeof(buf), "            const %s x%d_%d = __ldg(xi%d + (%d));\n", T, k, j - row[u], k, col[j]);
+                        s += buf;
+                    }
+                for (int k = 0; k < R; ++k)
+                    for (int j = row[u]; j < row[u + 1]; ++j) {
+                        const std::string v = lit(val[j]);
+                        snprintf(buf, sizeof(buf), "            sum%d = %s(sum%d, %s(%s, x%d_%d));\n", k, add, k, mul, v.c_str(), k, j - row[u]);
+                        s += buf;
+                    }
+            } else {
+                for (int k = 0; k < R; ++k) s += row_body(u, k, "            ");
+            }
+            s += "        } break;\n";
+        }
+        s += "        default: break;\n        }\n    } else {\n";
+    }
+    for (int k = 0; k < R; ++k) {
+        snprintf(buf, sizeof(buf), "        switch (u%d) {\n", k);
+        s += buf;
+        for (size_t u = 0; u + 1 < row.size(); ++u) {
+            s += "        case " + std::to_string(u) + ": {\n" + row_body(u, k, "            ") + "        } break;\n";
+        }
+        s += "        default: break;\n        }\n";
+    }
+    if (R > 1) s += "    }\n";
+    for (int k = 0; k < R; ++k) {
+        snprintf(buf, sizeof(buf), "    if (in%d) { const %s v = %s(alpha, sum%d); y[i%d] = append ? %s(yo%d, v) : v; }\n", k, T, mul, k, k, add, k);
+        s += buf;
+    }
+    s += "}\n";
     return s;
 }
 
@@ -242,7 +299,8 @@ static int launch_jit(vexb_ccsr *A, cudaStream_t st, const T *x, T *y, T alpha, 
     unsigned long long n = A->n;
     const void *idx = A->idx;
     void *args[] = {&n, &idx, &x, &y, &alpha, &append};
-    VEXB_TRY(jit_launch(A->jit_fn, (unsigned)((A->n + 255) / 256), 256, 0, st, args));
+    const size_t per_block = 256 * (size_t)ccsr_jit_rows_per_thread(A->hrow);
+    VEXB_TRY(jit_launch(A->jit_fn, (unsigned)((A->n + per_block - 1) / per_block), 256, 0, st, args));
     *done = true;
     return VEXB_OK;
 }

@@ -61,7 +61,7 @@ struct DistArgs {
     int rank, nparts;
     const int4 *push_blk; const int *send_cols; int n_push_blocks;
     // interior strip (hybrid ELL)
-    size_t n_int, pitch; int w_dyn, shift; const void *ell_col; const T *ell_val;
+    size_t n_int, pitch; int w_dyn; EllShifts shift; const void *ell_col; const T *ell_val;
     const int *tail_ptr, *tail_col; const T *tail_val; const int *int_row_ids; size_t y_off; int n_int_blocks;
     // boundary rows
     size_t b_n, b_pitch; int b_w; const int *b_col; const T *b_val; const int *b_rows; int n_bnd_blocks;
@@ -230,8 +230,16 @@ template <class T>
 __global__ void __launch_bounds__(1024) dot_fold_kernel(const T *__restrict__ parts, unsigned int n, T *result, PeerArgs pa,
                                                          unsigned long long *fault_host) {
     __shared__ T s_part[32];
+    // thread t adds partials t, t + 1024, ... in that order; the loads of 16 of them travel together (a plain loop waits
+    // for memory once per partial: 23 us for the 65 536 partials of a 256^3 product, 5 % of a CG iteration)
     T g = T(0);
-    for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) g = t_add<T>(g, parts[k]);
+    for (unsigned int k0 = threadIdx.x; k0 < n; k0 += 16u * blockDim.x) {
+        T v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { const unsigned int k = k0 + (unsigned)u * blockDim.x; v[u] = k < n ? parts[k] : T(0); }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { const unsigned int k = k0 + (unsigned)u * blockDim.x; if (k < n) g = t_add<T>(g, v[u]); }
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) g = t_add<T>(g, __shfl_down_sync(0xffffffffu, g, off));
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = g;
@@ -453,7 +461,7 @@ static int dist_apply_t(const vexb_dspmat *A, cudaStream_t st, const T *x, T *y,
     const vexb_spmat *S = A->loc;
     const bool fused_interior = S && S->fmt == VEXB_FMT_HELL && S->nnz > 0 && S->nrows_stored > 0;
     if (fused_interior) {
-        a.n_int = S->nrows_stored; a.pitch = S->ell_pitch; a.w_dyn = (int)S->ell_width; a.shift = S->ell_shift;
+        a.n_int = S->nrows_stored; a.pitch = S->ell_pitch; a.w_dyn = (int)S->ell_width; a.shift = S->ell_shifts;
         a.ell_col = S->ell_col16 ? (const void *)S->ell_col16 : (const void *)S->ell_col; a.ell_val = (const T *)S->ell_val;
         a.tail_ptr = S->tail_ptr; a.tail_col = S->tail_col; a.tail_val = (const T *)S->tail_val;
         a.int_row_ids = S->row_ids; a.y_off = S->y_offset;

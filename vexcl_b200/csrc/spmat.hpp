@@ -3,6 +3,14 @@
 #include "hostlogic.hpp"
 #include <vector>
 
+namespace vexb {
+// 16-bit ELL columns are stored as distances from (row + shift of the slot): one shift per ELL slot (a 7-point stencil
+// has its neighbours n*n, n, 1 away -- no single shift brings them all within 16 bits, one shift per slot does).  Slots
+// past the last entry share it.
+constexpr int kEllShiftSlots = 16;
+struct EllShifts { int s[kEllShiftSlots]; };
+}
+
 struct vexb_spmat {
     int dev = 0;
     int fmt = VEXB_FMT_CSR;
@@ -17,7 +25,7 @@ struct vexb_spmat {
     // HELL
     size_t ell_width = 0, ell_pitch = 0, tail_nnz = 0;
     int *ell_col = nullptr; void *ell_val = nullptr;
-    short *ell_col16 = nullptr; int ell_shift = 0;   // optional: columns as 16-bit offsets from (row + ell_shift); see spmv.col16
+    short *ell_col16 = nullptr; vexb::EllShifts ell_shifts = {};   // optional: columns as 16-bit offsets from (row + shift of the slot); see spmv.col16
     int *tail_ptr = nullptr; int *tail_col = nullptr; void *tail_val = nullptr;
     vexb_ccsr *patterns = nullptr; // VEXB_FMT_PATTERNS: the strip as unique row patterns + one pattern id per row (csrc/ccsr.cu)
     size_t n_patterns = 0;
@@ -33,7 +41,7 @@ namespace vexb {
 struct SpmvDesc {
     const void *ell_col; const void *ell_val; const int *tail_ptr; const int *tail_col; const void *tail_val;
     const int *rowptr; const int *col; const void *val;
-    unsigned long long pitch; int width; int shift;
+    unsigned long long pitch; int width; int shifts[kEllShiftSlots];
 };
 }
 

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kPipeThreads) csr_pipe_kernel(const int2 *__re
 }
 
 template <class T, int W, class C>
-__global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w_dyn, const C *__restrict__ ell_col, int shift,
+__global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w_dyn, const C *__restrict__ ell_col, const EllShifts shift,
                                                     const T *__restrict__ ell_val, const int *__restrict__ tail_ptr,
                                                     const int *__restrict__ tail_col, const T *__restrict__ tail_val,
                                                     const T *__restrict__ x, T *y, T alpha, int append,
@@ -382,11 +382,15 @@ __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w
 // of 4 * 66.  Per component the products are added in the same order as in hell_kernel (same bits).
 template <int K> struct MultiPtr { const void *x[K]; void *y[K]; };
 
+// The launch bound tells ptxas how many blocks per SM to plan for (K = 4: 3 blocks, up to 85 registers): with the default
+// it schedules for full occupancy at 40 registers and sinks the gathers between the products, i.e. waits for memory
+// three times per row.
 template <class T, int W, class C, int K>
-__global__ void __launch_bounds__(256) hell_multi_kernel(size_t n, size_t pitch, int w_dyn, const C *__restrict__ ell_col, int shift,
+__global__ void __launch_bounds__(256, (K >= 4 ? 3 : K == 3 ? 4 : 5)) hell_multi_kernel(size_t n, size_t pitch, int w_dyn, const C *__restrict__ ell_col, const EllShifts shift,
                                                           const T *__restrict__ ell_val, const int *__restrict__ tail_ptr,
                                                           const int *__restrict__ tail_col, const T *__restrict__ tail_val,
-                                                          MultiPtr<K> mp, T alpha, int append, const int *__restrict__ row_ids, size_t y_offset) {
+                                                          MultiPtr<K> mp, T alpha, int append, const int *__restrict__ row_ids, size_t y_offset,
+                                                          int flags) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
@@ -396,19 +400,24 @@ __global__ void __launch_bounds__(256) hell_multi_kernel(size_t n, size_t pitch,
     if (W > 0) {
         int c[W > 0 ? W : 1]; T v[W > 0 ? W : 1];
 #pragma unroll
-        for (int j = 0; j < W; ++j) { c[j] = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
+        for (int j = 0; j < W; ++j) { c[j] = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, ell_shift_of(shift, j)); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
+        // all K*W gathers are issued before the first product (one round trip for the whole row instead of K: the
+        // per-component loop the compiler otherwise keeps, at 40 registers, waits for memory K times)
+        T xv[K][W > 0 ? W : 1];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const T *x = static_cast<const T *>(mp.x[k]);
-            T xv[W > 0 ? W : 1];
 #pragma unroll
-            for (int j = 0; j < W; ++j) xv[j] = (c[j] != -1) ? ldg_keep(x + c[j], keep) : T(0);
+            for (int j = 0; j < W; ++j) xv[k][j] = (c[j] != -1) ? ((flags & 1) ? __ldg(x + c[j]) : ldg_keep(x + c[j], keep)) : T(0);
+        }
 #pragma unroll
-            for (int j = 0; j < W; ++j) if (c[j] != -1) sum[k] = t_add<T>(sum[k], t_mul<T>(v[j], xv[j]));
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int j = 0; j < W; ++j) if (c[j] != -1) sum[k] = t_add<T>(sum[k], t_mul<T>(v[j], xv[k][j]));
         }
     } else {
         for (int j = 0; j < w_dyn; ++j) {
-            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift);
+            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, ell_shift_of(shift, j));
             if (c != -1) {
                 const T v = ldg_stream(ell_val + i + (size_t)j * pitch, stream);
 #pragma unroll
@@ -425,7 +434,11 @@ __global__ void __launch_bounds__(256) hell_multi_kernel(size_t n, size_t pitch,
     }
     const size_t r = row_ids ? (size_t)row_ids[i] : i + y_offset;
 #pragma unroll
-    for (int k = 0; k < K; ++k) store_y<T>(static_cast<T *>(mp.y[k]), r, sum[k], alpha, append);
+    for (int k = 0; k < K; ++k) {
+        T *y = static_cast<T *>(mp.y[k]);
+        if (flags & 2) { const T v = t_mul<T>(alpha, sum[k]); __stcs(y + r, append ? t_add<T>(y[r], v) : v); }
+        else store_y<T>(y, r, sum[k], alpha, append);
+    }
 }
 
 // spmv.kernel = 3: one thread per row straight from the CSR arrays ("CSR-scalar").  Neighbouring lanes read
@@ -571,6 +584,152 @@ __global__ void __launch_bounds__(256, 4) csr_warp_kernel(const int2 *__restrict
         } else if (tn < n_tiles) issue(n0, n1);
         if (tn >= n_tiles) break;
         t = tn; d0 = n0; d1 = n1; n0 = m0; n1 = m1;
+    }
+}
+
+// ---- warp rings (spmv.kernel = 5) --------------------------------------------------------------------------------
+// The warp-tile kernel with the matrix stream taken off the warps' critical path.  Each warp is a persistent worker with a
+// private ring of `stages` shared-memory slots; lane 0 keeps stages-1 tiles ahead of the one being multiplied with TMA
+// bulk copies (cp.async.bulk -> UBLKCP) of the tile's val, col and row-pointer slices, each ring slot completing on its
+// own mbarrier.  While a warp waits for x gathers or adds up rows, its next tiles are already in flight -- the HBM stream
+// no longer stops when a warp does (the register-staged warp tiles reach 0.57 of the roofline on the irregular matrix:
+// a warp's loads are only in flight while that warp has nothing else to do).  There is no CTA-wide barrier anywhere:
+// warps drift apart freely.  Products are parked in place (over the staged values), rows are added from there by 1 / 4 /
+// 8 / 32 lanes per row exactly as in csr_warp_kernel, so the bits are the same.
+constexpr int kRingSlots = kWarpTileNnz + 8;             // aligned window of a tile: <= 256 + 3 + 3 entries
+constexpr int kRingRp = kWarpTileRows + 8;               // aligned window of its row pointers: <= 257 + 3 + 3 entries
+template <class T> struct RingStage {
+    static constexpr size_t val_bytes = (size_t)kRingSlots * sizeof(T);
+    static constexpr size_t col_bytes = (size_t)kRingSlots * 4;
+    static constexpr size_t rp_bytes = (size_t)kRingRp * 4;
+    static constexpr size_t bytes = (val_bytes + col_bytes + rp_bytes + 127) & ~(size_t)127;
+};
+
+template <class T, int G>
+__device__ __forceinline__ void ring_rows(const T *prod, const int *rp, int r0, int nr, int ja, int lane, T *y, T alpha,
+                                          int append, const int *__restrict__ row_ids) {
+    constexpr int RPW = 32 / G;
+    const int sub = lane % G, grp = lane / G;
+    for (int rb = 0; rb < nr; rb += RPW) {
+        const int r = rb + grp;
+        T s = T(0);
+        if (r < nr) {
+            const int a = rp[r] - ja, b = rp[r + 1] - ja;
+            for (int j = a + sub; j < b; j += G) s = t_add<T>(s, prod[j]);
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) s = t_add<T>(s, __shfl_down_sync(0xffffffffu, s, off, G));
+        }
+        if (r < nr && sub == 0) store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, s, alpha, append);
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256, 3) csr_ring_kernel(const int2 *__restrict__ tile, int n_tiles, const int *__restrict__ rowptr,
+                                                       const int *__restrict__ col, const T *__restrict__ val,
+                                                       const T *__restrict__ x, T *y, T alpha, int append,
+                                                       const int *__restrict__ row_ids, int stages) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned char *ring = smem + (size_t)warp * stages * RingStage<T>::bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)nwarps * stages * RingStage<T>::bytes) + warp * stages;
+    const int total_warps = gridDim.x * nwarps;
+    const int t0 = blockIdx.x * nwarps + warp;
+    if (t0 >= n_tiles) return;
+    const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + s)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // lane 0: start the copies of one tile into ring slot s (nothing to copy for a row longer than a tile)
+    auto issue = [&](int2 e0, int2 e1, int s) {
+        const int r0 = e0.x, nr = e1.x - e0.x, j0 = e0.y, cnt = e1.y - e0.y;
+        if (cnt > kWarpTileNnz || nr <= 0 || cnt <= 0) return;
+        const int ja = j0 & ~3, je = (j0 + cnt + 3) & ~3;
+        const int ra = r0 & ~3, re = (r0 + nr + 1 + 3) & ~3;
+        unsigned char *base = ring + (size_t)s * RingStage<T>::bytes;
+        const uint32_t bv = (uint32_t)(je - ja) * (uint32_t)sizeof(T), bc = (uint32_t)(je - ja) * 4u, br = (uint32_t)(re - ra) * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bars + s)), "r"(bv + bc + br) : "memory");
+        bulk_g2s(base, val + ja, bv, bars + s, stream);
+        bulk_g2s(base + RingStage<T>::val_bytes, col + ja, bc, bars + s, stream);
+        bulk_g2s(base + RingStage<T>::val_bytes + RingStage<T>::col_bytes, rowptr + ra, br, bars + s, stream);
+    };
+    auto desc = [&](int t, int2 &e0, int2 &e1) {
+        if (t < n_tiles) { e0 = __ldg(tile + t); e1 = __ldg(tile + t + 1); } else { e0 = make_int2(0, 0); e1 = e0; }
+    };
+
+    // prologue: tiles 0 .. stages-2 of this warp go out; the descriptor of the tile to issue next is kept in registers
+    int2 c0, c1, q0, q1;
+    desc(t0, c0, c1);                                                   // current tile
+    {
+        int2 e0 = c0, e1 = c1;
+        for (int k = 0; k < stages - 1; ++k) {
+            const int t = t0 + k * total_warps;
+            if (t >= n_tiles) break;
+            if (k > 0) desc(t, e0, e1);
+            if (lane == 0) issue(e0, e1, k);
+        }
+    }
+    desc(t0 + (stages - 1) * total_warps, q0, q1);                      // next tile to issue
+    unsigned phase = 0;                                                  // bit s: parity to wait for on ring slot s
+    int it = 0;
+    for (int t = t0; t < n_tiles; t += total_warps, ++it) {
+        const int s = it % stages;
+        // keep the ring full: the slot tile `it-1` just left takes tile `it + stages-1`
+        {
+            const int tq = t + (stages - 1) * total_warps;
+            if (tq < n_tiles && lane == 0) issue(q0, q1, (it + stages - 1) % stages);
+        }
+        int2 n0, n1;
+        desc(t + total_warps, n0, n1);                                  // next tile to multiply (already in flight)
+        int2 m0, m1;
+        desc(t + stages * total_warps, m0, m1);                         // tile to issue in the next iteration
+        const int r0 = c0.x, nr = c1.x - c0.x, j0 = c0.y, cnt = c1.y - c0.y;
+        if (cnt > kWarpTileNnz) {
+            // one long row: the warp strides over it straight from global memory
+            T sacc = T(0);
+            for (int j = j0 + lane; j < j0 + cnt; j += 32) sacc = t_add<T>(sacc, t_mul<T>(ldg_stream(val + j, stream), ldg_keep(x + ldg_stream(col + j, stream), keep)));
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sacc = t_add<T>(sacc, __shfl_down_sync(0xffffffffu, sacc, off));
+            if (lane == 0) store_y<T>(y, row_ids ? (size_t)row_ids[r0] : (size_t)r0, sacc, alpha, append);
+        } else if (nr > 0 && cnt <= 0) {
+            // empty rows only
+            for (int r = lane; r < nr; r += 32) store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, T(0), alpha, append);
+        } else if (nr > 0) {
+            mbar_wait(bars + s, (phase >> s) & 1u);
+            phase ^= 1u << s;
+            unsigned char *base = ring + (size_t)s * RingStage<T>::bytes;
+            T *val_s = reinterpret_cast<T *>(base);
+            const int *col_s = reinterpret_cast<const int *>(base + RingStage<T>::val_bytes);
+            const int *rp_s = reinterpret_cast<const int *>(base + RingStage<T>::val_bytes + RingStage<T>::col_bytes);
+            const int ja = j0 & ~3, lo = j0 - ja;
+            T xv[kWarpPer];
+#pragma unroll
+            for (int k = 0; k < kWarpPer; ++k) {
+                const int j = lane + 32 * k;
+                xv[k] = (j < cnt) ? ldg_keep(x + col_s[lo + j], keep) : T(0);
+            }
+#pragma unroll
+            for (int k = 0; k < kWarpPer; ++k) {
+                const int j = lane + 32 * k;
+                if (j < cnt) val_s[lo + j] = t_mul<T>(val_s[lo + j], xv[k]);
+            }
+            __syncwarp();
+            const int *rp = rp_s + (r0 - (r0 & ~3));
+            switch (warp_tile_group(cnt, nr)) {
+                case 1:  ring_rows<T, 1>(val_s, rp, r0, nr, ja, lane, y, alpha, append, row_ids); break;
+                case 4:  ring_rows<T, 4>(val_s, rp, r0, nr, ja, lane, y, alpha, append, row_ids); break;
+                case 8:  ring_rows<T, 8>(val_s, rp, r0, nr, ja, lane, y, alpha, append, row_ids); break;
+                default: ring_rows<T, 32>(val_s, rp, r0, nr, ja, lane, y, alpha, append, row_ids); break;
+            }
+            // the slot is reused by a bulk copy in the next iteration: order this warp's generic-proxy accesses before it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+        c0 = n0; c1 = n1; q0 = m0; q1 = m1;
     }
 }
 
@@ -728,38 +887,81 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
         std::vector<int> ecol(pitch * w, -1);               // sentinel (col_t)(-1): hybrid_ell.inl:139
         std::vector<T> eval(pitch * w, T(0));
         std::vector<int> tptr(n + 1, 0), tcol; std::vector<T> tval;
+        // Slot alignment.  The reference packs a row's entries into slots 0, 1, ... (hybrid_ell.inl:139-144).  A row with
+        // fewer than w entries may keep them in ANY increasing sequence of slots -- the kernels walk the slots in order and
+        // skip padding, so the products are still added in storage order and y has the same bits.  Short rows (grid
+        // boundaries: an identity row, a stencil with a neighbour missing) are therefore placed so that each entry
+        // lands in the slot where full rows keep the entry at the same distance from the diagonal.  Every slot then
+        // holds ONE distance on a structured grid, whatever the grid size, which is what lets the 16-bit column
+        // encoding below (one shift per slot) cover 7-point stencils on 256^3 and 512^3 points: 10 instead of 12 bytes per
+        // stored entry.  vexb_spmat_hell_download compacts rows to the left again (the reference's packing).
+        std::vector<long long> ref(w, 0);
+        bool have_ref = false;
+        if (param("spmv.slot_align", 1)) {
+            for (size_t i = 0; i < n && !have_ref; ++i)
+                if ((size_t)(rowptr[i + 1] - rowptr[i]) >= w && w > 0) {
+                    for (size_t k = 0; k < w; ++k) ref[k] = (long long)col[rowptr[i] + k] - (long long)i;
+                    have_ref = true;
+                }
+        }
         for (size_t i = 0; i < n; ++i) {
-            size_t cntw = 0;
-            for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
-                if (cntw < w) { ecol[i + pitch * cntw] = col[j]; eval[i + pitch * cntw] = val[j]; ++cntw; }
-                else { tcol.push_back(col[j]); tval.push_back(val[j]); }
+            const int b = rowptr[i], cnt = rowptr[i + 1] - b;
+            if (have_ref && cnt > 0 && (size_t)cnt < w) {
+                size_t s0 = 0;
+                for (int q = 0; q < cnt; ++q) {
+                    const long long d = (long long)col[b + q] - (long long)i;
+                    const size_t last = w - (size_t)(cnt - q);        // latest slot that leaves room for the entries after this one
+                    size_t t = s0;
+                    bool found = false;
+                    for (size_t c = s0; c <= last && !found; ++c) if (ref[c] == d) { t = c; found = true; }
+                    for (size_t c = s0; c <= last && !found; ++c) if (std::llabs(ref[c] - d) <= 16384) { t = c; found = true; }
+                    ecol[i + pitch * t] = col[b + q]; eval[i + pitch * t] = val[b + q];
+                    s0 = t + 1;
+                }
+            } else {
+                size_t cntw = 0;
+                for (int j = b; j < rowptr[i + 1]; ++j) {
+                    if (cntw < w) { ecol[i + pitch * cntw] = col[j]; eval[i + pitch * cntw] = val[j]; ++cntw; }
+                    else { tcol.push_back(col[j]); tval.push_back(val[j]); }
+                }
             }
             tptr[i + 1] = (int)tcol.size();
         }
         A->tail_nnz = tcol.size();
         VEXB_TRY(upload(eval, 0, &A->ell_val, &A->device_bytes));
         if (param("spmv.col16", 1) && w > 0) {
-            // Banded matrices: every stored column lies within +-32767 of (row + shift) for one shift per strip, so
-            // the ELL columns fit 16 bits.  The kernel then streams 10 instead of 12 bytes per stored entry
+            // Banded matrices: the stored columns of ELL slot k lie within +-32767 of (row + shift[k]) for one shift per
+            // slot, so the ELL columns fit 16 bits.  The kernel then streams 10 instead of 12 bytes per stored entry
             // (measured on configs[2]: 0.098 ms against 0.110 ms per product, profiles/r02_variant_probe.json); same
-            // bits in y, only the index encoding differs.  spmv.col16 = 0 keeps 32-bit columns.
-            long long lo = 0, hi = 0; bool any = false;
-            for (size_t k = 0; k < w; ++k)
+            // bits in y, only the index encoding differs.  One shift per slot (not per strip) is what admits stencils
+            // on 3-D grids: the k-th neighbour of every row is the same distance away (+-n*n for a 7-point stencil on
+            // n^3 points), whatever that distance is.  Strips wider than kEllShiftSlots share the last shift among the
+            // remaining slots.  spmv.col16 = 0 keeps 32-bit columns.
+            std::vector<long long> lo(kEllShiftSlots, 0), hi(kEllShiftSlots, 0);
+            std::vector<char> any(kEllShiftSlots, 0);
+            for (size_t k = 0; k < w; ++k) {
+                const size_t g = std::min<size_t>(k, kEllShiftSlots - 1);
                 for (size_t i = 0; i < n; ++i) {
                     const int c = ecol[i + pitch * k];
                     if (c < 0) continue;
                     const long long d = (long long)c - (long long)i;
-                    if (!any) { lo = hi = d; any = true; } else { lo = std::min(lo, d); hi = std::max(hi, d); }
+                    if (!any[g]) { lo[g] = hi[g] = d; any[g] = 1; } else { lo[g] = std::min(lo[g], d); hi[g] = std::max(hi[g], d); }
                 }
-            if (any && hi - lo <= 65534) {
-                const long long shift = lo + 32767;
+            }
+            bool fits = false, ok = true;
+            for (int g = 0; g < kEllShiftSlots; ++g) if (any[g]) { fits = true; if (hi[g] - lo[g] > 65534) ok = false; }
+            if (fits && ok) {
+                EllShifts sh;
+                for (int g = 0; g < kEllShiftSlots; ++g) sh.s[g] = any[g] ? (int)(lo[g] + 32767) : 0;
                 std::vector<short> e16(pitch * w, (short)-32768);
-                for (size_t k = 0; k < w; ++k)
+                for (size_t k = 0; k < w; ++k) {
+                    const long long shift = sh.s[std::min<size_t>(k, kEllShiftSlots - 1)];
                     for (size_t i = 0; i < n; ++i) {
                         const int c = ecol[i + pitch * k];
                         if (c >= 0) e16[i + pitch * k] = (short)((long long)c - (long long)i - shift);
                     }
-                A->ell_shift = (int)shift;
+                }
+                A->ell_shifts = sh;
                 VEXB_TRY(upload(e16, 0, (void **)&A->ell_col16, &A->device_bytes));
             }
         }
@@ -787,10 +989,31 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
     }
     if (A->fmt == VEXB_FMT_PATTERNS) return vexb_ccsr_spmv(A->dev, (void *)st, A->patterns, x, y, (double)alpha, append);
     // spmv.kernel: 0 = TMA-staged one-shot CTA tiles, 1 = persistent TMA pipeline, 2 = register-staged CTA tiles, 3 = thread per row,
-    //              4 = warp tiles; unset (-1) = the strip's own choice (build(): 3 for short even rows, else 4)
+    //              4 = warp tiles, 5 = warp rings (TMA); unset (-1) = the strip's own choice (build(): 3 for short even rows, else 4)
     long variant = param("spmv.kernel", param("spmv.pipeline", 0) ? 1 : -1);
     if (variant < 0) variant = A->csr_variant;
-    if (A->fmt == VEXB_FMT_CSR && variant == 4) {
+    if (A->fmt == VEXB_FMT_CSR && variant == 5) {
+        long stages = std::max(2l, std::min(param("spmv.ring_stages", 3), 8l));
+        long warps = std::max(1l, std::min(param("spmv.ring_warps", 8), 8l));
+        const size_t smem = (size_t)warps * stages * RingStage<T>::bytes + (size_t)warps * stages * 8;
+        static std::atomic<unsigned long long> attr_set[2];
+        const int ti = sizeof(T) == 8 ? 0 : 1;
+        const unsigned long long bit = 1ull << (A->dev & 63);
+        if (!(attr_set[ti].load() & bit)) {
+            VEXB_CUDA(cudaFuncSetAttribute(csr_ring_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            attr_set[ti].fetch_or(bit);
+        }
+        VEXB_CHECK(smem <= 224 * 1024, "spmv.ring_stages x spmv.ring_warps needs %zu bytes of shared memory", smem);
+        int per_sm = 0;
+        VEXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_ring_kernel<T>, (int)warps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        const long cap = param("spmv.ctas_per_sm", 0);
+        if (cap > 0 && per_sm > cap) per_sm = (int)cap;
+        const size_t grid = std::min((A->n_wtiles + warps - 1) / warps, (size_t)per_sm * (size_t)sm_count(A->dev));
+        csr_ring_kernel<T><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(A->wtile, (int)A->n_wtiles, A->rowptr, A->col, (const T *)A->val, x, y,
+                                                                             alpha, append, A->row_ids, (int)stages);
+        VEXB_LAUNCHED();
+    } else if (A->fmt == VEXB_FMT_CSR && variant == 4) {
         static std::atomic<int> per_sm[2];
         const int ti = sizeof(T) == 8 ? 0 : 1;
         if (!per_sm[ti].load()) {
@@ -849,9 +1072,9 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
     } else {
         const unsigned blocks = (unsigned)((n + 255) / 256);
 #define HL(W) do { \
-            if (A->ell_col16) hell_kernel<T, W, short><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col16, A->ell_shift, \
+            if (A->ell_col16) hell_kernel<T, W, short><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col16, A->ell_shifts, \
                   (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, x, y, alpha, append, A->row_ids); \
-            else hell_kernel<T, W, int><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col, 0, \
+            else hell_kernel<T, W, int><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col, EllShifts{}, \
                   (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, x, y, alpha, append, A->row_ids); } while (0)
         switch (A->ell_width) {
             case 1: HL(1); break; case 2: HL(2); break; case 3: HL(3); break; case 4: HL(4); break;
@@ -871,11 +1094,12 @@ static int spmv_multi_launch(const vexb_spmat *A, cudaStream_t st, const void *c
     MultiPtr<K> mp;
     for (int k = 0; k < K; ++k) { mp.x[k] = x[k]; mp.y[k] = y[k]; }
     const unsigned blocks = (unsigned)((n + 255) / 256);
+    const int mflags = (int)param("spmv.multi_flags", 0);   // 1: gathers of x without the L2 evict-last hint, 2: streaming stores of y
 #define HM(W) do { \
-        if (A->ell_col16) hell_multi_kernel<T, W, short, K><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col16, A->ell_shift, \
-              (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, mp, alpha, append, A->row_ids, A->y_offset); \
-        else hell_multi_kernel<T, W, int, K><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col, 0, \
-              (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, mp, alpha, append, A->row_ids, A->y_offset); } while (0)
+        if (A->ell_col16) hell_multi_kernel<T, W, short, K><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col16, A->ell_shifts, \
+              (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, mp, alpha, append, A->row_ids, A->y_offset, mflags); \
+        else hell_multi_kernel<T, W, int, K><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col, EllShifts{}, \
+              (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, mp, alpha, append, A->row_ids, A->y_offset, mflags); } while (0)
     switch (A->ell_width) {
         case 3: HM(3); break; case 5: HM(5); break; case 7: HM(7); break;
         default: HM(0); break;
@@ -906,7 +1130,8 @@ int vexb::spmat_from_csr(int dev, size_t nrows, size_t ncols, std::vector<int> &
         d.ell_col = A->ell_col16 ? (const void *)A->ell_col16 : (const void *)A->ell_col; d.ell_val = A->ell_val;
         d.tail_ptr = A->tail_ptr; d.tail_col = A->tail_col; d.tail_val = A->tail_val;
         d.rowptr = A->rowptr; d.col = A->col; d.val = A->val;
-        d.pitch = A->ell_pitch; d.width = (int)A->ell_width; d.shift = A->ell_shift;
+        d.pitch = A->ell_pitch; d.width = (int)A->ell_width;
+        for (int g = 0; g < kEllShiftSlots; ++g) d.shifts[g] = A->ell_shifts.s[g];
         cudaError_t e = cudaMalloc(&A->d_desc, sizeof(d));
         if (e == cudaSuccess) e = cudaMemcpy(A->d_desc, &d, sizeof(d), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { set_error(__FILE__, __LINE__, "strip descriptor upload failed: %s", cudaGetErrorString(e)); st = VEXB_ERR_CUDA; }
@@ -1016,10 +1241,27 @@ extern "C" int vexb_spmat_hell_download(const vexb_spmat *A, int32_t *ell_col, v
         for (size_t k = 0; k < A->ell_width; ++k)
             for (size_t i = 0; i < A->ell_pitch; ++i) {
                 const short raw = e16[i + A->ell_pitch * k];
-                ell_col[i + A->ell_pitch * k] = raw == (short)-32768 ? -1 : (int32_t)((long long)i + A->ell_shift + raw);
+                ell_col[i + A->ell_pitch * k] = raw == (short)-32768 ? -1 : (int32_t)((long long)i + A->ell_shifts.s[std::min<size_t>(k, vexb::kEllShiftSlots - 1)] + raw);
             }
     }
     if (ell_val && ne) VEXB_CUDA(cudaMemcpy(ell_val, A->ell_val, ne * vs, cudaMemcpyDeviceToHost));
+    if (ell_col && ell_val && ne) {
+        // the reference's packing: a row's entries in slots 0, 1, ... (the device layout may leave gaps, see build())
+        for (size_t i = 0; i < A->nrows_stored; ++i) {
+            size_t dst = 0;
+            for (size_t k = 0; k < A->ell_width; ++k) {
+                const size_t at = i + A->ell_pitch * k;
+                if (ell_col[at] == -1) continue;
+                const size_t to = i + A->ell_pitch * dst;
+                if (to != at) {
+                    ell_col[to] = ell_col[at]; ell_col[at] = -1;
+                    memcpy((char *)ell_val + to * vs, (char *)ell_val + at * vs, vs);
+                    memset((char *)ell_val + at * vs, 0, vs);
+                }
+                ++dst;
+            }
+        }
+    }
     if (csr_ptr) {
         if (A->tail_nnz) {
             std::vector<int> tp(A->nrows_stored + 1);

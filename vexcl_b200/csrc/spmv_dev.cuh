@@ -2,6 +2,7 @@
 // streaming / keeping loads, the ELL row body.
 #pragma once
 #include "common.cuh"
+#include "spmat.hpp"
 
 namespace vexb {
 
@@ -42,8 +43,9 @@ __device__ __forceinline__ short ldg_stream(const short *p, uint64_t policy) {
     short v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(policy)); return v;
 }
 // Column of an ELL slot.  32-bit storage holds it directly (-1 = padding); 16-bit storage (spmv.col16) holds its
-// distance from (row + shift), with -32768 = padding: 2 bytes less HBM traffic per stored entry for banded matrices.
+// distance from (row + shift of its slot), with -32768 = padding: 2 bytes less HBM traffic per stored entry for banded matrices.
 __device__ __forceinline__ int ell_column(int raw, size_t, int) { return raw; }
+__device__ __forceinline__ int ell_shift_of(const EllShifts &sh, int slot) { return sh.s[slot < kEllShiftSlots ? slot : kEllShiftSlots - 1]; }
 __device__ __forceinline__ int ell_column(short raw, size_t row, int shift) { return raw == (short)-32768 ? -1 : (int)row + shift + (int)raw; }
 __device__ __forceinline__ double ldg_stream(const double *p, uint64_t policy) {
     double v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy)); return v;
@@ -61,7 +63,7 @@ __device__ __forceinline__ void store_y(T *y, size_t r, T sum, T alpha, int appe
 // One row of a hybrid-ELL strip (hybrid_ell.inl:252-268): ELL slots in order, then the CSR tail; products and sums rounded
 // separately.  W > 0: fully unrolled, all 2W streaming loads and then the W gathers of x in flight at once.
 template <class T, int W, class C>
-__device__ __forceinline__ T hell_row_sum(size_t i, size_t pitch, int w_dyn, const C *__restrict__ ell_col, int shift,
+__device__ __forceinline__ T hell_row_sum(size_t i, size_t pitch, int w_dyn, const C *__restrict__ ell_col, const EllShifts &shift,
                                           const T *__restrict__ ell_val, const int *__restrict__ tail_ptr,
                                           const int *__restrict__ tail_col, const T *__restrict__ tail_val,
                                           const T *__restrict__ x, uint64_t stream, uint64_t keep) {
@@ -69,7 +71,7 @@ __device__ __forceinline__ T hell_row_sum(size_t i, size_t pitch, int w_dyn, con
     if (W > 0) {
         int c[W > 0 ? W : 1]; T v[W > 0 ? W : 1]; T xv[W > 0 ? W : 1];
 #pragma unroll
-        for (int j = 0; j < W; ++j) { c[j] = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
+        for (int j = 0; j < W; ++j) { c[j] = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, ell_shift_of(shift, j)); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
 #pragma unroll
         for (int j = 0; j < W; ++j) xv[j] = (c[j] != -1) ? ldg_keep(x + c[j], keep) : T(0);
 #pragma unroll
@@ -79,7 +81,7 @@ __device__ __forceinline__ T hell_row_sum(size_t i, size_t pitch, int w_dyn, con
         // (4.2 vs 3.3 TB/s effective at average width 12): occupancy hides the latency, and a padded slot
         // (column -1) costs 4 bytes, not 12, because its value is never fetched.
         for (int j = 0; j < w_dyn; ++j) {
-            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift);
+            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, ell_shift_of(shift, j));
             if (c != -1) sum = t_add<T>(sum, t_mul<T>(ldg_stream(ell_val + i + (size_t)j * pitch, stream), ldg_keep(x + c, keep)));
         }
     }

@@ -46,15 +46,24 @@ __global__ void __launch_bounds__(ST_THREADS) stencil_kernel(const T *__restrict
     const int rhalo = width - 1 - center;
 
     // ---- stage the window: position p holds X(b0 - center + p) --------------------------------------------------
-    for (int p = threadIdx.x; p < wlen; p += ST_THREADS) {
+    // Eight loads per thread are issued before the first store (addresses selected without branches: end clamps and
+    // halo buffers are pointer selects).  A load -> store loop leaves one load in flight per thread -- ncu showed 57 % of
+    // the stall samples on those stores (profiles/r02_ncu_summary_before.md) and the kernel at 0.41 of either bound.
+    auto source = [&](int p) -> const T * {
         const long long j = b0 - center + p;
-        T v;
-        if (j < 0) v = left ? left[center + j] : x[0];
-        else if (j >= n) {
+        if (j < 0) return left ? left + (center + j) : x;
+        if (j >= n) {
             const long long r = j - n;
-            v = (right && rhalo > 0) ? right[r < rhalo ? r : rhalo - 1] : x[n - 1];
-        } else v = x[j];
-        win[st_pad(p)] = v;
+            return (right && rhalo > 0) ? right + (r < rhalo ? r : rhalo - 1) : x + (n - 1);
+        }
+        return x + j;
+    };
+    for (int p0 = threadIdx.x; p0 < wlen; p0 += 8 * ST_THREADS) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int p = p0 + u * ST_THREADS; v[u] = *source(p < wlen ? p : wlen - 1); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int p = p0 + u * ST_THREADS; if (p < wlen) win[st_pad(p)] = v[u]; }
     }
     for (int k = threadIdx.x; k < st_ceil8(width); k += ST_THREADS) taps[k] = k < width ? s[k] : T(0);
     __syncthreads();
