@@ -656,7 +656,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 def bench_csr_kernels(ctx, vx, gen, A_csr, x, y, nbytes, args, barrier, peak):
     """The CSR kernels of csrc/spmv.cu (what vex::sparse::csr and format=csr use; SpMat's AUTO picks hybrid ELL for these
     matrices as the reference does): configs[2] forced to CSR, and an irregular matrix (4M rows, widths U[0,32))."""
-    names = {-1: "default", 3: "thread_per_row", 4: "warp_tiles", 5: "warp_rings_tma", 0: "tma_cta_tiles"}
+    names = {-1: "default", 3: "thread_per_row", 4: "warp_tiles", 5: "warp_rings_tma", 6: "cta_tiles_x_window", 0: "tma_cta_tiles"}
     steps = max(args.steps, 20)
     out = {}
 

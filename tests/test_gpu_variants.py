@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 
 
 # spmv.kernel: 0 = TMA-staged CTA tiles, 1 = persistent TMA pipeline, 2 = register-staged CTA tiles, 3 = thread per row,
-# 4 = warp tiles, 5 = warp rings (per-warp TMA ring), -1 = the strip's own choice
-@pytest.fixture(params=[3, 4, 5, 0, 1, 2, -1])
+# 4 = warp tiles, 5 = warp rings (per-warp TMA ring), 6 = CTA tiles with the x window in shared memory, -1 = the strip's own choice
+@pytest.fixture(params=[3, 4, 5, 6, 0, 1, 2, -1])
 def csr_kernel(request, built):
     vx.set_param("spmv.kernel", request.param)
     yield request.param

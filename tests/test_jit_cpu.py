@@ -53,7 +53,7 @@ def test_user_function_source_and_nvrtc_compile(env):
     i = fake_vec(1024, np.int32, 0x9000)
     src = jit_source(api, L, i, L.ADD, greater(x, 0.5) + (i << 2))
     assert "return (int)((int)lhs[i] + (int)" in src and "NVRTC: ok" in src
-    assert "a3 = vexb_elem(tt, lhs, i + 3 * stride, off)" in src           # four elements per thread in flight
+    assert "a3 = vexb_elem(tt, lhs, i + 768ull, off)" in src               # four elements per thread in flight, one contiguous chunk per block
     # every operator family compiles
     f = fake_vec(1024, np.float32, 0xa000)
     e = vx.if_else(x > y, vx.sin(x) * vx.pow_(y, 2.0), vx.fmin(x, y)) + vx.fma(x, y, z) - vx.fabs(-x) + f * i + vx.ElementIndex(3) % 7

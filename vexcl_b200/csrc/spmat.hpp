@@ -19,6 +19,7 @@ struct vexb_spmat {
     // CSR stream
     void *val = nullptr; int *col = nullptr; int *rowptr = nullptr; int2 *tile = nullptr;
     size_t n_tiles = 0, tile_nnz = 0, tile_rows = 0;
+    int2 *tile_x = nullptr; size_t xwin = 0, n_windowed_tiles = 0;   // per CTA tile: {first column, length} of its x window (csr_window_kernel)
     int2 *wtile = nullptr; size_t n_wtiles = 0;   // warp tiles (<= 256 nnz, <= 256 rows) for csr_warp_kernel
     int csr_variant = 0;                          // kernel picked for this strip when spmv.kernel is not set (see build())
     size_t max_row_nnz = 0;

@@ -56,6 +56,14 @@ __device__ __forceinline__ void phase_a_products(T *val_s, const int *col_s, con
     }
 }
 
+__device__ __forceinline__ void mbar_wait_fwd(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
 // Shared-memory carve-up (dynamic): [val: (tile_nnz+8)*sizeof(T)] [col: (tile_nnz+8)*4] [rp: (tile_rows+12)*4] [mbarrier]
 template <class T>
 __global__ void __launch_bounds__(256) csr_stream_kernel(const int2 *__restrict__ tile, const int *__restrict__ rowptr,
@@ -117,6 +125,106 @@ __global__ void __launch_bounds__(256) csr_stream_kernel(const int2 *__restrict_
     phase_a_products<T, 8>(val_s, col_s, x, lo, cnt, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
     // phase B
+    const int *rp = rp_s + (r0 - r0a);
+    if (cnt <= 12 * nr) {
+        for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+            const int a = rp[r] - j0a, b = rp[r + 1] - j0a;
+            T s = T(0);
+            for (int j = a; j < b; ++j) s = t_add<T>(s, val_s[j]);
+            store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, s, alpha, append);
+        }
+    } else {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int r = warp; r < nr; r += nw) {
+            const int a = rp[r] - j0a, b = rp[r + 1] - j0a;
+            T s = T(0);
+            for (int j = a + lane; j < b; j += 32) s = t_add<T>(s, val_s[j]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s = t_add<T>(s, __shfl_down_sync(0xffffffffu, s, off));
+            if (lane == 0) store_y<T>(y, row_ids ? (size_t)row_ids[r0 + r] : (size_t)r0 + r, s, alpha, append);
+        }
+    }
+}
+
+// ---- CTA tiles with a staged x window (spmv.kernel = 6) ----------------------------------------------------------
+// On matrices whose rows scatter over a band (every nonzero in its own 128-byte line of x) the gathers, not HBM, bound
+// every kernel above: the L1 tag stage takes one line per cycle per SM, a warp-wide gather 32 of them (ncu on the 4M-row
+// irregular matrix: L1 at 82 %, DRAM at 43 %, profiles/r02_ncu_summary_before.md).  Here the tile's slice of x -- columns
+// [cmin, cmax] of its nonzeros, found on the host -- is one more TMA bulk copy into shared memory, and phase A gathers
+// from there: a handful of bank conflicts instead of 32 tag lookups.  The window is read from L2 (x stays resident),
+// HBM traffic is unchanged.  Tiles whose window would not fit (tile_x.y == 0) gather from global memory as before.
+// Everything else is csr_stream_kernel: row-block tiles, val/col/row_ptr staged by TMA, products in place, rows added
+// in storage order.
+template <class T>
+__global__ void __launch_bounds__(256) csr_window_kernel(const int2 *__restrict__ tile, const int2 *__restrict__ tile_x,
+                                                         const int *__restrict__ rowptr, const int *__restrict__ col,
+                                                         const T *__restrict__ val, const T *__restrict__ x, T *y, T alpha,
+                                                         int append, int tile_nnz, int tile_rows, int xwin,
+                                                         const int *__restrict__ row_ids) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    T *val_s = reinterpret_cast<T *>(smem);
+    T *x_s = val_s + (tile_nnz + 8);
+    int *col_s = reinterpret_cast<int *>(x_s + (xwin + 4));
+    int *rp_s = col_s + (tile_nnz + 8);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(rp_s + (tile_rows + 12));
+
+    const int2 t0 = tile[blockIdx.x], t1 = tile[blockIdx.x + 1];
+    const int2 tx = tile_x[blockIdx.x];                  // {first column of the window (even), its length (0: no window)}
+    const int r0 = t0.x, nr = t1.x - t0.x;
+    const int j0 = t0.y, cnt = t1.y - t0.y;
+    if (nr <= 0) return;
+
+    if (cnt > tile_nnz) {
+        // one long row: the whole CTA strides over it straight from global memory
+        T s = T(0);
+        for (int j = j0 + threadIdx.x; j < j0 + cnt; j += blockDim.x) s = t_add<T>(s, t_mul<T>(val[j], x[col[j]]));
+        __shared__ T red[8];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s = t_add<T>(s, __shfl_down_sync(0xffffffffu, s, off));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T tot = red[0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) tot = t_add<T>(tot, red[w]);
+            store_y<T>(y, row_ids ? (size_t)row_ids[r0] : (size_t)r0, tot, alpha, append);
+        }
+        return;
+    }
+
+    const int j0a = j0 & ~3, j1a = (j0 + cnt + 3) & ~3;
+    const int r0a = r0 & ~3, r1a = (r0 + nr + 1 + 3) & ~3;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bv = (uint32_t)(j1a - j0a) * (uint32_t)sizeof(T);
+        const uint32_t bc = (uint32_t)(j1a - j0a) * 4u;
+        const uint32_t br = (uint32_t)(r1a - r0a) * 4u;
+        const uint32_t bx = (uint32_t)tx.y * (uint32_t)sizeof(T);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bv + bc + br + bx) : "memory");
+        const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
+        if (bx) bulk_g2s(x_s, x + tx.x, bx, bar, keep);
+        if (bv) { bulk_g2s(val_s, val + j0a, bv, bar, stream); bulk_g2s(col_s, col + j0a, bc, bar, stream); }
+        bulk_g2s(rp_s, rowptr + r0a, br, bar, stream);
+    }
+    __syncthreads();
+    mbar_wait_fwd(bar, 0u);
+    const int lo = j0 - j0a;
+    if (tx.y) {
+        // phase A from the window: val_s[j] *= x_s[col_s[j] - first column]
+        const int hi = lo + cnt, cb = tx.x, nt = (int)blockDim.x;
+        for (int j = lo + (int)threadIdx.x; j < hi; j += nt * 8) {
+            int c[8]; T xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int jj = j + u * nt; c[u] = jj < hi ? col_s[jj] - cb : 0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = x_s[c[u]];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int jj = j + u * nt; if (jj < hi) val_s[jj] = t_mul<T>(val_s[jj], xv[u]); }
+        }
+    } else {
+        phase_a_products<T, 8>(val_s, col_s, x, lo, cnt, (int)threadIdx.x, (int)blockDim.x);
+    }
+    __syncthreads();
     const int *rp = rp_s + (r0 - r0a);
     if (cnt <= 12 * nr) {
         for (int r = threadIdx.x; r < nr; r += blockDim.x) {
@@ -382,11 +490,12 @@ __global__ void __launch_bounds__(256) hell_kernel(size_t n, size_t pitch, int w
 // of 4 * 66.  Per component the products are added in the same order as in hell_kernel (same bits).
 template <int K> struct MultiPtr { const void *x[K]; void *y[K]; };
 
-// The launch bound tells ptxas how many blocks per SM to plan for (K = 4: 3 blocks, up to 85 registers): with the default
-// it schedules for full occupancy at 40 registers and sinks the gathers between the products, i.e. waits for memory
-// three times per row.
+// Measured (profiles/r02_probe_multi_rhs.md): telling ptxas to plan for 3 blocks per SM (64 registers, all K*W gathers
+// issued before the first product) is SLOWER than its default schedule at 40 registers and 6 blocks per SM (0.213 against
+// 0.197 ms for K = 4 on configs[2]); the L2 hints on x and streaming stores of y make no difference.  ncu shows no unit
+// above 70 % -- DRAM is simply idle 31 % of the time -- so occupancy, not instruction order, is what this kernel runs on.
 template <class T, int W, class C, int K>
-__global__ void __launch_bounds__(256, (K >= 4 ? 3 : K == 3 ? 4 : 5)) hell_multi_kernel(size_t n, size_t pitch, int w_dyn, const C *__restrict__ ell_col, const EllShifts shift,
+__global__ void __launch_bounds__(256) hell_multi_kernel(size_t n, size_t pitch, int w_dyn, const C *__restrict__ ell_col, const EllShifts shift,
                                                           const T *__restrict__ ell_val, const int *__restrict__ tail_ptr,
                                                           const int *__restrict__ tail_col, const T *__restrict__ tail_val,
                                                           MultiPtr<K> mp, T alpha, int append, const int *__restrict__ row_ids, size_t y_offset,
@@ -857,6 +966,27 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
         tiles.push_back(make_int2((int)n, rowptr[n]));
         A->n_tiles = tiles.size() - 1;
         VEXB_TRY(upload(tiles, 0, (void **)&A->tile, &A->device_bytes));
+        // x window of every tile for csr_window_kernel: columns [cmin, cmax] of its nonzeros, start aligned down to 16
+        // bytes (bulk copy), length rounded up likewise; {0, 0} when it exceeds spmv.xwin entries or would pass the end of x
+        {
+            long xw = param("spmv.xwin", 2048);
+            xw = std::max(64l, std::min(xw, 8192l)) & ~3l;
+            A->xwin = (size_t)xw;
+            std::vector<int2> tx(A->n_tiles, make_int2(0, 0));
+            size_t windowed = 0;
+            for (size_t t = 0; t < A->n_tiles; ++t) {
+                const int a = tiles[t].y, b = tiles[t + 1].y;
+                if (b <= a || b - a > tn) continue;
+                int cmin = col[a], cmax = col[a];
+                for (int j = a + 1; j < b; ++j) { cmin = std::min(cmin, col[j]); cmax = std::max(cmax, col[j]); }
+                const int G = (int)(16 / sizeof(T));                   // bulk copies move multiples of 16 bytes from 16-byte aligned addresses
+                const int c0 = cmin & ~(G - 1);
+                const int len = (cmax - c0 + 1 + G - 1) & ~(G - 1);
+                if (len <= xw && (size_t)c0 + (size_t)len <= A->ncols) { tx[t] = make_int2(c0, len); ++windowed; }   // never past the end of x
+            }
+            A->n_windowed_tiles = windowed;
+            VEXB_TRY(upload(tx, 0, (void **)&A->tile_x, &A->device_bytes));
+        }
         // warp tiles for csr_warp_kernel: <= 256 nnz and <= 256 rows, cut at row boundaries; a longer row is its own tile
         std::vector<int2> wt;
         size_t maxw = 0;
@@ -877,6 +1007,8 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
         // against 0.76 for the TMA tile kernel, profiles/r02_variant_probe.json).  Anything else: warp tiles.
         const double mean = n ? (double)A->nnz / (double)n : 0.0;
         A->csr_variant = (mean <= 16.0 && (double)maxw <= 2.0 * mean + 2.0) ? 3 : 4;
+        // scattered rows inside a band: CTA tiles with the x window in shared memory (when nearly every tile has one)
+        if (A->csr_variant == 4 && param("spmv.auto_window", 1) && A->n_windowed_tiles * 10 >= A->n_tiles * 9) A->csr_variant = 6;
         VEXB_TRY(upload(rowptr, 16, (void **)&A->rowptr, &A->device_bytes));
         VEXB_TRY(upload(col, 16, (void **)&A->col, &A->device_bytes));
         VEXB_TRY(upload(val, 16, &A->val, &A->device_bytes));
@@ -989,10 +1121,23 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
     }
     if (A->fmt == VEXB_FMT_PATTERNS) return vexb_ccsr_spmv(A->dev, (void *)st, A->patterns, x, y, (double)alpha, append);
     // spmv.kernel: 0 = TMA-staged one-shot CTA tiles, 1 = persistent TMA pipeline, 2 = register-staged CTA tiles, 3 = thread per row,
-    //              4 = warp tiles, 5 = warp rings (TMA); unset (-1) = the strip's own choice (build(): 3 for short even rows, else 4)
+    //              4 = warp tiles, 5 = warp rings (TMA), 6 = CTA tiles with the x window in shared memory; unset (-1) = the strip's own choice (build(): 3 for short even rows, else 4)
     long variant = param("spmv.kernel", param("spmv.pipeline", 0) ? 1 : -1);
     if (variant < 0) variant = A->csr_variant;
-    if (A->fmt == VEXB_FMT_CSR && variant == 5) {
+    if (A->fmt == VEXB_FMT_CSR && variant == 6 && (reinterpret_cast<uintptr_t>(x) & 15) != 0) variant = 4;   // the window copy needs a 16-byte aligned x
+    if (A->fmt == VEXB_FMT_CSR && variant == 6) {
+        const size_t smem = (A->tile_nnz + 8) * sizeof(T) + (A->xwin + 4) * sizeof(T) + (A->tile_nnz + 8) * 4 + (A->tile_rows + 12) * 4 + 16;
+        static std::atomic<unsigned long long> attr_set[2];
+        const int ti = sizeof(T) == 8 ? 0 : 1;
+        const unsigned long long bit = 1ull << (A->dev & 63);
+        if (smem > 48 * 1024 && !(attr_set[ti].load() & bit)) {
+            VEXB_CUDA(cudaFuncSetAttribute(csr_window_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[ti].fetch_or(bit);
+        }
+        csr_window_kernel<T><<<(unsigned)A->n_tiles, 256, smem, st>>>(A->tile, A->tile_x, A->rowptr, A->col, (const T *)A->val, x, y, alpha, append,
+                                                                     (int)A->tile_nnz, (int)A->tile_rows, (int)A->xwin, A->row_ids);
+        VEXB_LAUNCHED();
+    } else if (A->fmt == VEXB_FMT_CSR && variant == 5) {
         long stages = std::max(2l, std::min(param("spmv.ring_stages", 3), 8l));
         long warps = std::max(1l, std::min(param("spmv.ring_warps", 8), 8l));
         const size_t smem = (size_t)warps * stages * RingStage<T>::bytes + (size_t)warps * stages * 8;
@@ -1178,7 +1323,7 @@ extern "C" int vexb_spmat_destroy(vexb_spmat *A) {
     if (!A) return VEXB_OK;
     VEXB_RELEASE_GUARD();
     DeviceGuard g(A->dev);
-    cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile); cudaFree(A->wtile); cudaFree(A->d_desc);
+    cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile); cudaFree(A->tile_x); cudaFree(A->wtile); cudaFree(A->d_desc);
     vexb_ccsr_destroy(A->patterns);
     cudaFree(A->row_ids); cudaFree(A->ell_col); cudaFree(A->ell_col16); cudaFree(A->ell_val); cudaFree(A->tail_ptr); cudaFree(A->tail_col); cudaFree(A->tail_val);
     delete A;
