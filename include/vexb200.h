@@ -244,6 +244,12 @@ int vexb_jit_pending(int *pending);
  * vexb_eval of a new shape does in the default mode).  Needs NVRTC, no device.  A process may exit while background
  * compilations run: the thread that started them waits for the one in flight and cancels the rest on its way out. */
 int vexb_jit_precompile(int lhs_dtype, int assign_op, const vexb_expr *expr, int background);
+/* All components of a multi-expression assignment in one launch (assign_multiexpression, operations.hpp:2081-2185):
+ * lhs[k][i] OP= exprs[k](i), k < ncomp <= 8, all of one type; every right-hand side of element i is evaluated before
+ * any left-hand side of element i is written.  *handled = 0 when the request is not served here (NVRTC missing or
+ * still compiling in the background, sparse-product terminals): evaluate component by component then. */
+int vexb_eval_multi(int dev, void *stream, int ncomp, void *const *lhs, int lhs_dtype, int assign_op,
+                    const vexb_expr *const *exprs, size_t n, size_t index_offset, int *handled);
 /* Which kernel vexb_eval would take for this request: writes a short
  * name ("sweep:muladd", "interp", "jit", ...) to buf. */
 int vexb_eval_path(int lhs_dtype, int assign_op, const vexb_expr *expr, char *buf, size_t buflen);

@@ -101,6 +101,25 @@ void assign_components(const std::array<vex::vector<T>*, N> &lhs, const Rhs &rhs
         }
     }, std::make_index_sequence<N>());
 
+    // One generated kernel for all components (vexb_eval_multi): reads of element i all happen before its writes, so no
+    // temporaries whatever reads what.  Served once the kernel for this tuple of expressions exists (it is compiled in
+    // the background at first use); until then -- and for anything it does not take -- component by component below.
+    {
+        bool fused = N >= 2 && N <= 8;
+        for (unsigned d = 0; d < nd && fused; ++d) {
+            const void *es[N]; void *out[N];
+            for (size_t i = 0; i < N; ++i) { es[i] = &ir[i * nd + d].e; out[i] = (*lhs[i])(d).raw(); }
+            int handled = 0;
+            VEXB_CHECKED(vexb_eval_multi(queue[d].ordinal(), queue[d].raw(), (int)N, out, dtype_of<T>::value, OP::op,
+                                         reinterpret_cast<const vexb_expr *const *>(es), lhs[0]->part_size(d), lhs[0]->part_start(d), &handled));
+            if (!handled) {
+                // all devices or none: a kernel that is ready is ready for every device, so only d == 0 can say no
+                fused = false;
+            }
+        }
+        if (fused) return;
+    }
+
     bool hazard = false;                                              // does component j > i read what component i writes?
     for (size_t i = 0; i < N && !hazard; ++i)
         for (size_t j = i + 1; j < N && !hazard; ++j)

@@ -2,7 +2,7 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference``
 legs may import this package.  vexcl_b200/ never does (tests/test_no_oracle_in_product.py
-checks that).
+checks the sources and the library's dynamic dependencies).
 
 Two halves:
   * oracle.c  (liboracle.so, gcc + OpenMP): floating-point loops -- elementwise chunks,

@@ -118,3 +118,40 @@ def test_compound_shift_uses_the_left_operand_type(ctx1):
             assert np.array_equal(u.read(), A.astype(np.uint32) >> Bc)
         finally:
             vx.set_param("eval.jit", 2)
+
+
+@pytest.mark.parametrize("nparts", [1, 2])
+def test_multi_expression_assignment_in_one_kernel(ctx1, ctx2, nparts):
+    """vex::tie(x, y) = std::tie(x + y, y - x) and friends through vexb_eval_multi: one generated kernel for all
+    components, right-hand sides evaluated before any target is written (assign_multiexpression,
+    vexcl/operations.hpp:2081-2185, tests/multivector_arithmetics.cpp).  Same bits as component by component."""
+    import ctypes as C
+    import time
+    ctx = {1: ctx1, 2: ctx2}[nparts]
+    n = 100_003
+    X, Y, Z = (oracle.uniform_real(s, n) for s in (41, 42, 43))
+    vx.set_param("eval.jit", 1)                               # compile at once: the fused kernel serves the first call
+    try:
+        x, y, z = vx.vector(ctx, X), vx.vector(ctx, Y), vx.vector(ctx, Z)
+        assert vx.assign_multi([x, y], [x + y, y - x]) is True          # each component reads what the other writes
+        assert np.array_equal(x.read(), X + Y) and np.array_equal(y.read(), Y - X)
+        n0 = vx.launch_count()
+        assert vx.assign_multi([x, y, z], [vx.sin(x) * 2.0 + z, x * y - z / 3.0, vx.sqrt(vx.fabs(y)) + x], L.ADD) is True
+        assert vx.launch_count() - n0 == ctx.nparts                     # one launch per device slice
+        x0, y0, z0 = X + Y, Y - X, Z
+        want = (x0 + (np.sin(x0) * 2.0 + z0), y0 + (x0 * y0 - z0 / 3.0), z0 + (np.sqrt(np.abs(y0)) + x0))
+        for got, w in zip((x, y, z), want):
+            assert np.allclose(got.read(), w, rtol=1e-14, atol=0)
+    finally:
+        vx.set_param("eval.jit", 2)
+    # default mode: the first call is served component by component while the kernel compiles, later calls are fused
+    a, b = vx.vector(ctx, X), vx.vector(ctx, Y)
+    first = vx.assign_multi([a, b], [a * 3.0 - b, b * a + 1.5])
+    assert np.array_equal(a.read(), X * 3.0 - Y) and np.array_equal(b.read(), Y * X + 1.5)
+    pend, t0 = C.c_int(1), time.time()
+    while pend.value and time.time() - t0 < 60:
+        L.check(L.lib().vexb_jit_pending(C.byref(pend)))
+    a.write(X); b.write(Y)
+    assert vx.assign_multi([a, b], [a * 3.0 - b, b * a + 1.5]) is True
+    assert np.array_equal(a.read(), X * 3.0 - Y) and np.array_equal(b.read(), Y * X + 1.5)
+    assert first in (True, False)

@@ -113,6 +113,7 @@ def lib():
         "vexb_d2d": ([i, vp, vp, sz, vp], i), "vexb_memset": ([i, vp, i, sz, vp], i),
         "vexb_partition": ([sz, i, P(d), P(sz)], i),
         "vexb_eval": ([i, vp, vp, i, i, P(Expr), sz, sz], i),
+        "vexb_eval_multi": ([i, vp, i, P(vp), i, i, P(P(Expr)), sz, sz, P(i)], i),
         "vexb_eval_path": ([i, i, P(Expr), C.c_char_p, sz], i),
         "vexb_function_register": ([C.c_char_p, i, i, P(i), C.c_char_p, P(i)], i),
         "vexb_jit_source": ([i, i, P(Expr), C.c_char_p, P(sz), i], i),

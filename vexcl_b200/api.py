@@ -1302,3 +1302,42 @@ class Graph:
                 L.lib().vexb_graph_destroy(g)
         except Exception:
             pass
+
+
+def assign_multi(lhs, rhs, op: int = L.SET) -> bool:
+    """vex::tie(lhs...) OP= std::tie(rhs...) (assign_multiexpression, vexcl/operations.hpp:2081-2185): every right-hand side is
+    evaluated before any left-hand side is written.  One generated kernel per device slice when the back end has it
+    (vexb_eval_multi; compiled in the background at the first use of the tuple of expressions), else component by
+    component through temporaries.  Returns True when the fused kernel ran."""
+    lhs, rhs = list(lhs), [wrap(r) for r in rhs]
+    if len(lhs) != len(rhs) or not lhs:
+        raise ValueError("assign_multi: one expression per target")
+    ctx, n, dt = lhs[0].ctx, lhs[0].n, lhs[0].dtype
+    if any(v.ctx is not ctx or v.n != n or v.dtype != dt for v in lhs):
+        raise ValueError("assign_multi: targets must share context, size and type")
+    lib = L.lib()
+    N = len(lhs)
+    fused = 2 <= N <= 8
+    for k in ctx.local:
+        if not fused:
+            break
+        lows = []
+        for r in rhs:
+            low = _Lowering(k, lhs[0].part_start(k))
+            low.size = n
+            low.lower(r)
+            lows.append(low)
+        es = (C.POINTER(L.Expr) * N)(*[C.pointer(low.e) for low in lows])
+        out = (C.c_void_p * N)(*[v.bufs[k] for v in lhs])
+        handled = C.c_int(0)
+        L.check(lib.vexb_eval_multi(ctx.devs[k], ctx.streams[k], N, out, dt, op, es, lhs[0].part_size(k), lhs[0].part_start(k), C.byref(handled)))
+        if not handled.value:
+            fused = False                       # the kernel is not there yet (first slice says so): nothing has been written
+    if fused:
+        return True
+    tmp = [vector(ctx, n, dtype=lhs[0].np_dtype) for _ in range(N)]
+    for t, r in zip(tmp, rhs):
+        t.assign(r)
+    for v, t in zip(lhs, tmp):
+        v._assign(op, t)
+    return False

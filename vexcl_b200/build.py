@@ -74,7 +74,7 @@ def build_lib(force: bool = False, verbose_ptxas: bool = False) -> Path:
 
 def build_oracle(force: bool = False) -> Path:
     if force or _stale(ORACLE_LIB, [ORACLE_SRC]):
-        _run(["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c11",
+        _run(["gcc", "-O3", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c11",
               "-Wall", "-o", ORACLE_LIB, ORACLE_SRC, "-lm"])
     return ORACLE_LIB
 

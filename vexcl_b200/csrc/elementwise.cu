@@ -10,10 +10,13 @@
 //        (2) everything else runs the IR interpreter (expr_eval.cuh).
 // Both are pure HBM streams; neither contracts mul+add into FMA.
 #include "expr_eval.cuh"
+#include <vector>
 #include "shapes.cuh"
 
 namespace vexb {
 
+int jit_eval_multi(int dev, cudaStream_t st, int ncomp, void *const *lhs, int lhs_dtype, int aop, const vexb_expr *const *es,
+                   size_t n, size_t index_offset, int mode, bool *done);
 int jit_eval(int dev, cudaStream_t st, void *lhs, int lhs_dtype, int aop, const vexb_expr &e, size_t n, size_t index_offset,
              int mode, bool *done);
 
@@ -241,5 +244,37 @@ extern "C" int vexb_eval(int dev, void *stream, void *lhs, int lhs_dtype, int as
     const int blocks = (int)(want < cap ? want : cap);
     interp_kernel<4><<<blocks, 256, 0, st>>>(prog, lhs, lhs_dtype, n, index_offset);
     VEXB_LAUNCHED();
+    return VEXB_OK;
+}
+
+// All components of a multi-expression assignment in one launch (assign_multiexpression, vexcl/operations.hpp:2081-2185):
+// lhs[k][i] OP= expr_k(i) for k < ncomp, every right-hand side of element i evaluated before any left-hand side of
+// element i is written (so components may read what other components write, as in vex::tie(x, y) = (x + y, y - x)).
+// Served by a kernel generated for the tuple of expressions (NVRTC, compiled in the background at first use like any
+// other new shape).  *handled = 0: not served (NVRTC absent, still compiling, a sparse product among the terminals, more
+// than 8 components) -- the caller evaluates component by component, staging through temporaries where needed.
+extern "C" int vexb_eval_multi(int dev, void *stream, int ncomp, void *const *lhs, int lhs_dtype, int assign_op,
+                               const vexb_expr *const *exprs, size_t n, size_t index_offset, int *handled) {
+    VEXB_CHECK(handled, "handled is NULL");
+    *handled = 0;
+    VEXB_CHECK(ncomp >= 1 && lhs && exprs, "bad arguments");
+    VEXB_CHECK(lhs_dtype >= VEXB_F64 && lhs_dtype <= VEXB_U64, "bad lhs dtype %d", lhs_dtype);
+    VEXB_CHECK(assign_op >= VEXB_SET && assign_op <= VEXB_RSH, "bad assign op %d", assign_op);
+    if (ncomp < 2 || ncomp > 8) return VEXB_OK;
+    std::vector<vexb_expr> es((size_t)ncomp);
+    std::vector<const vexb_expr *> ps((size_t)ncomp);
+    for (int c = 0; c < ncomp; ++c) {
+        VEXB_CHECK(exprs[c], "expression %d is NULL", c);
+        VEXB_TRY(normalize_expr(exprs[c], &es[(size_t)c], n != 0));
+        ps[(size_t)c] = &es[(size_t)c];
+    }
+    if (n == 0) { *handled = 1; return VEXB_OK; }
+    for (int c = 0; c < ncomp; ++c) VEXB_CHECK(lhs[c] != nullptr, "lhs %d is NULL", c);
+    const long jit_mode = param("eval.force_interp", 0) ? param("eval.jit", 0) : param("eval.jit", 2);
+    if (!jit_mode || !param("eval.fuse_multi", 1)) return VEXB_OK;
+    DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
+    bool done = false;
+    VEXB_TRY(jit_eval_multi(dev, (cudaStream_t)stream, ncomp, lhs, lhs_dtype, assign_op, ps.data(), n, index_offset, (int)jit_mode, &done));
+    *handled = done ? 1 : 0;
     return VEXB_OK;
 }
