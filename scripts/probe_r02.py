@@ -65,8 +65,45 @@ if "ring" in what:
         out[label] = res
         del A, x, y, y4
 
-if "multi" in what or "p3d" in what:
-    pass
+if "window" in what:
+    # csr_window_kernel (spmv.kernel=6): tile size and window size are read when the matrix is built
+    for label, gaps in (("irregular 4M U[0,32) gaps U[1,64)", 64), ("irregular 4M U[0,32) gaps U[1,8)", 8)):
+        row, col, val = gen.irregular_rows(4_000_000, 0, 32, seed=1, max_gap=gaps)
+        n = row.size - 1
+        nb = gen.spmv_bytes(n, n, int(row[-1]))
+        x, y, y4 = vx.vector(ctx, n), vx.vector(ctx, n), vx.vector(ctx, n)
+        x.assign(vx.ElementIndex() * (1.0 / n) + 0.5)
+        res = {}
+        ref = None
+        for tn, xw in ((2048, 2048), (1024, 2048), (4096, 4096), (2048, 4096), (1024, 1024)):
+            vx.set_param("spmv.tile_nnz", tn); vx.set_param("spmv.xwin", xw)
+            A = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_CSR)
+            if ref is None:
+                vx.set_param("spmv.kernel", 4)
+                A.apply(x, y4, 1.0, False)
+                ref = y4.read()
+                for k in (3, 4):
+                    vx.set_param("spmv.kernel", k)
+                    ms = timeit(lambda: A.apply(x, y, 1.0, False))
+                    res[f"kernel={k}"] = {"ms": ms, "frac": nb / ms / 1e6 / PEAK}
+                vx.set_param("spmv.kernel", -1)
+                res["default_variant_ms"] = timeit(lambda: A.apply(x, y, 1.0, False))
+            vx.set_param("spmv.kernel", 6)
+            y.assign(0.0)
+            A.apply(x, y, 1.0, False)
+            got = y.read()
+            err = float(np.max(np.abs(got - ref) / (np.abs(ref) + 1e-300)))
+            ms = timeit(lambda: A.apply(x, y, 1.0, False))
+            res[f"kernel=6 tile_nnz={tn} xwin={xw}"] = {"ms": ms, "frac": nb / ms / 1e6 / PEAK, "max_rel_diff_vs_warp_tiles": err}
+            vx.set_param("spmv.kernel", -1)
+            del A
+        vx.set_param("spmv.tile_nnz", 2048); vx.set_param("spmv.xwin", 2048)
+        Ah = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_AUTO)
+        ms = timeit(lambda: Ah.apply(x, y, 1.0, False))
+        res["spmat_auto"] = {"ms": ms, "frac": nb / ms / 1e6 / PEAK, "fmt": int(Ah.info().loc.fmt)}
+        del Ah
+        out[label] = res
+        del x, y, y4
 
 if "multi" in what:
     row, col, val = gen.poisson_strip(2, 3162)

@@ -121,6 +121,39 @@ BOOST_AUTO_TEST_CASE(tied_vectors_read_before_write)      // operations.hpp:2238
     }
 }
 
+BOOST_AUTO_TEST_CASE(multiexpression_in_one_kernel)       // assign_multiexpression, operations.hpp:2081-2185: one launch per device
+{
+    const size_t n = 4096;
+    std::vector<double> x = random_vector<double>(n), y = random_vector<double>(n);
+    vex::vector<double> X(ctx, x), Y(ctx, y);
+    vexb_set_param("eval.jit", 1);                        // compile at once, so that the first assignment is already fused
+    uint64_t l0 = 0, l1 = 0;
+    vexb_launch_count(&l0);
+    vex::tie(X, Y) = std::make_tuple(X + Y, Y - X);       // reads of element i before its writes: no temporaries
+    vexb_launch_count(&l1);
+    vexb_set_param("eval.jit", 2);
+    BOOST_CHECK(l1 - l0 == ctx.size());
+    std::vector<double> rx(n), ry(n);
+    copy(X, rx); copy(Y, ry);
+    for (size_t i = 0; i < n; ++i) { BOOST_CHECK(rx[i] == x[i] + y[i]); BOOST_CHECK(ry[i] == y[i] - x[i]); }
+    // compound assignment on three components, mixed functions
+    vex::multivector<double, 3> m(ctx, n);
+    m(0) = X; m(1) = Y; m(2) = 0.5;
+    vexb_set_param("eval.jit", 1);
+    vexb_launch_count(&l0);
+    m += std::tie(sin(m(1)) * 2, m(0) * m(2), m(0) - m(1));
+    vexb_launch_count(&l1);
+    vexb_set_param("eval.jit", 2);
+    BOOST_CHECK(l1 - l0 == ctx.size());
+    std::vector<double> h(3 * n);
+    copy(m, h);
+    for (size_t i = 0; i < n; ++i) {
+        BOOST_CHECK_CLOSE(h[i], rx[i] + sin(ry[i]) * 2, 1e-12);
+        BOOST_CHECK(h[n + i] == ry[i] + rx[i] * 0.5);
+        BOOST_CHECK(h[2 * n + i] == 0.5 + (rx[i] - ry[i]));
+    }
+}
+
 BOOST_AUTO_TEST_CASE(builtin_functions)                   // :78-92
 {
     typedef std::array<double, 2> elem_t;

@@ -94,18 +94,20 @@ def poisson_ccsr(n: int, index_dtype=np.uint64, col_dtype=np.int32):
     return idx, row, col, val
 
 
-def irregular_rows(n: int, lo: int = 0, hi: int = 32, seed: int = 1, index_dtype=np.int64):
-    """An irregular square matrix: row widths U[lo, hi), columns ascending within a row (random gaps of 1..63 starting
-    about half a row's span left of the diagonal, clipped to the matrix), values U[-0.5, 0.5).  Returns (row, col, val)."""
+def irregular_rows(n: int, lo: int = 0, hi: int = 32, seed: int = 1, index_dtype=np.int64, max_gap: int = 64):
+    """An irregular square matrix: row widths U[lo, hi), columns ascending within a row (random gaps of 1..max_gap-1
+    starting about half a row's span left of the diagonal, clipped to the matrix), values U[-0.5, 0.5).  max_gap = 64:
+    every nonzero's x value in its own 128-byte line (scattered); max_gap = 8: a few per line (clustered, FEM-like).
+    Returns (row, col, val)."""
     rng = np.random.default_rng(seed)
     w = rng.integers(lo, hi, n)
     row = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(w, out=row[1:])
     nnz = int(row[-1])
-    gaps = rng.integers(1, 64, nnz)
+    gaps = rng.integers(1, max_gap, nnz)
     run = np.cumsum(gaps)
     start = np.repeat(run[row[:-1].clip(max=max(nnz - 1, 0))] - gaps[row[:-1].clip(max=max(nnz - 1, 0))], w) if nnz else np.empty(0, np.int64)
-    base = np.repeat(np.arange(n, dtype=np.int64) - 16 * w, w)
+    base = np.repeat(np.arange(n, dtype=np.int64) - (max_gap // 4) * w, w)
     col = np.clip(base + (run - start), 0, n - 1)
     return row.astype(index_dtype), col.astype(index_dtype), rng.random(nnz) - 0.5
 
