@@ -510,23 +510,21 @@ __global__ void __launch_bounds__(256) hell_multi_kernel(size_t n, size_t pitch,
         int c[W > 0 ? W : 1]; T v[W > 0 ? W : 1];
 #pragma unroll
         for (int j = 0; j < W; ++j) { c[j] = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, ell_shift_of(shift, j)); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
-        // all K*W gathers are issued before the first product (one round trip for the whole row instead of K: the
-        // per-component loop the compiler otherwise keeps, at 40 registers, waits for memory K times)
-        T xv[K][W > 0 ? W : 1];
+        // one component at a time (W gathers in flight, then that component's products).  Issuing all K*W gathers first
+        // was measured slower, with the default register budget (0.215 ms) as well as with 64 registers (0.213 ms),
+        // against 0.197 ms for this order at K = 4 on configs[2]
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const T *x = static_cast<const T *>(mp.x[k]);
+            T xv[W > 0 ? W : 1];
 #pragma unroll
-            for (int j = 0; j < W; ++j) xv[k][j] = (c[j] != -1) ? ((flags & 1) ? __ldg(x + c[j]) : ldg_keep(x + c[j], keep)) : T(0);
-        }
+            for (int j = 0; j < W; ++j) xv[j] = (c[j] != -1) ? ((flags & 1) ? __ldg(x + c[j]) : ldg_keep(x + c[j], keep)) : T(0);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-#pragma unroll
-            for (int j = 0; j < W; ++j) if (c[j] != -1) sum[k] = t_add<T>(sum[k], t_mul<T>(v[j], xv[k][j]));
+            for (int j = 0; j < W; ++j) if (c[j] != -1) sum[k] = t_add<T>(sum[k], t_mul<T>(v[j], xv[j]));
         }
     } else {
         for (int j = 0; j < w_dyn; ++j) {
-            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, ell_shift_of(shift, j));
+            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift.s[0]);   // run-time widths: one shift for all slots (build())
             if (c != -1) {
                 const T v = ldg_stream(ell_val + i + (size_t)j * pitch, stream);
 #pragma unroll
@@ -1001,14 +999,17 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
         for (size_t i = 0; i < n; ++i) maxw = std::max(maxw, (size_t)(rowptr[i + 1] - rowptr[i]));
         A->n_wtiles = wt.size() - 1; A->max_row_nnz = maxw;
         VEXB_TRY(upload(wt, 0, (void **)&A->wtile, &A->device_bytes));
-        // Kernel for this strip unless spmv.kernel says otherwise.  Short, even rows (max <= 2 x mean, mean <= 16): one
+        // Kernel for this strip unless spmv.kernel says otherwise.  Short, even rows (max <= 2 x mean, mean <= 8): one
         // thread per row straight from the CSR arrays (csr_scalar_kernel) -- every lane always has loads in flight and the
         // sectors a warp touches are used up within a few iterations (measured 0.98 of the HBM roofline on 5-point Poisson
-        // against 0.76 for the TMA tile kernel, profiles/r02_variant_probe.json).  Anything else: warp tiles.
+        // against 0.76 for the TMA tile kernel, profiles/r02_variant_probe.json).  Anything else: warp tiles (widths
+        // U[0,32), mean 15.5: 0.22 ms against 0.27 ms for thread per row, profiles/r02_probe_window.json).
         const double mean = n ? (double)A->nnz / (double)n : 0.0;
-        A->csr_variant = (mean <= 16.0 && (double)maxw <= 2.0 * mean + 2.0) ? 3 : 4;
-        // scattered rows inside a band: CTA tiles with the x window in shared memory (when nearly every tile has one)
-        if (A->csr_variant == 4 && param("spmv.auto_window", 1) && A->n_windowed_tiles * 10 >= A->n_tiles * 9) A->csr_variant = 6;
+        A->csr_variant = (mean <= 8.0 && (double)maxw <= 2.0 * mean + 2.0) ? 3 : 4;
+        // CTA tiles with the x window in shared memory stay opt-in (spmv.kernel = 6 or spmv.auto_window = 1): measured at
+        // 0.46 ms on the 4M-row irregular matrix against 0.22 ms for warp tiles (profiles/r02_probe_window.json) -- the
+        // one-shot CTA (copy, wait, multiply, add up) costs more than the L1 tag lookups it saves
+        if (A->csr_variant == 4 && param("spmv.auto_window", 0) && A->n_windowed_tiles * 10 >= A->n_tiles * 9) A->csr_variant = 6;
         VEXB_TRY(upload(rowptr, 16, (void **)&A->rowptr, &A->device_bytes));
         VEXB_TRY(upload(col, 16, (void **)&A->col, &A->device_bytes));
         VEXB_TRY(upload(val, 16, &A->val, &A->device_bytes));
@@ -1071,8 +1072,12 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
             // remaining slots.  spmv.col16 = 0 keeps 32-bit columns.
             std::vector<long long> lo(kEllShiftSlots, 0), hi(kEllShiftSlots, 0);
             std::vector<char> any(kEllShiftSlots, 0);
+            // Widths above 9 run the kernels' run-time loop over the slots, which cannot index the by-value shift table
+            // without spilling it to local memory (measured: 0.33 instead of 0.19 ms on a width-21 strip): such strips
+            // use ONE shift for all slots, as in round 1 (g = 0 for every slot).
+            const bool per_slot = w <= 9;
             for (size_t k = 0; k < w; ++k) {
-                const size_t g = std::min<size_t>(k, kEllShiftSlots - 1);
+                const size_t g = per_slot ? std::min<size_t>(k, kEllShiftSlots - 1) : 0;
                 for (size_t i = 0; i < n; ++i) {
                     const int c = ecol[i + pitch * k];
                     if (c < 0) continue;
@@ -1084,7 +1089,7 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
             for (int g = 0; g < kEllShiftSlots; ++g) if (any[g]) { fits = true; if (hi[g] - lo[g] > 65534) ok = false; }
             if (fits && ok) {
                 EllShifts sh;
-                for (int g = 0; g < kEllShiftSlots; ++g) sh.s[g] = any[g] ? (int)(lo[g] + 32767) : 0;
+                for (int g = 0; g < kEllShiftSlots; ++g) sh.s[g] = any[per_slot ? g : 0] ? (int)(lo[per_slot ? g : 0] + 32767) : 0;
                 std::vector<short> e16(pitch * w, (short)-32768);
                 for (size_t k = 0; k < w; ++k) {
                     const long long shift = sh.s[std::min<size_t>(k, kEllShiftSlots - 1)];

@@ -81,7 +81,7 @@ __device__ __forceinline__ T hell_row_sum(size_t i, size_t pitch, int w_dyn, con
         // (4.2 vs 3.3 TB/s effective at average width 12): occupancy hides the latency, and a padded slot
         // (column -1) costs 4 bytes, not 12, because its value is never fetched.
         for (int j = 0; j < w_dyn; ++j) {
-            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, ell_shift_of(shift, j));
+            const int c = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, shift.s[0]);   // run-time widths use one shift (spmv.cu build())
             if (c != -1) sum = t_add<T>(sum, t_mul<T>(ldg_stream(ell_val + i + (size_t)j * pitch, stream), ldg_keep(x + c, keep)));
         }
     }
