@@ -316,6 +316,13 @@ def bench_strong(ctx, vx, L, gen, rank, world, args, barrier, allmax, allsum, pe
             g = Graph(ctx, step)
             msg = allmax(time_loop(ctx, g.launch, steps, args.warmup, barrier)) / steps
             res["us_per_product_cuda_graph"] = msg * 1e3
+            # ten products per graph launch: what an iterative solver replaying whole iterations sees -- one host launch per
+            # ten products, so the figure no longer contains the host's enqueue rate (Python, ~10 us per call)
+            g10 = Graph(ctx, lambda: [step() for _ in range(10)])
+            ms10 = allmax(time_loop(ctx, g10.launch, max(steps // 10, 5), 2, barrier)) / max(steps // 10, 5) / 10
+            res["us_per_product_cuda_graph_of_10"] = ms10 * 1e3
+            res["frac_of_aggregate_hbm_peak_cuda_graph_of_10"] = nbytes / (ms10 * 1e-3) / 1e9 / (peak * world)
+            del g10
             msf = allmax(time_flushed(ctx, g.launch, steps, 3, barrier, flusher)) / steps
             res["us_per_product_l2_flushed"] = msf * 1e3
             res["gbs_l2_flushed"] = nbytes / (msf * 1e-3) / 1e9

@@ -114,12 +114,8 @@ if "multi" in what:
     for r, v in enumerate(xs):
         v.assign(vx.ElementIndex() * (1.0 / N) + 0.25 * r)
     one = timeit(lambda: A.apply(xs[0], ys[0], 1.0, False))
-    res = {"ms_one": one}
-    for fl in (0, 1, 2, 3):
-        vx.set_param("spmv.multi_flags", fl)
-        four = timeit(lambda: A.apply_multi(xs, ys, 1.0, False))
-        res[f"flags={fl}"] = {"ms_four": four, "ratio": four / one}
-    vx.set_param("spmv.multi_flags", 0)
+    four = timeit(lambda: A.apply_multi(xs, ys, 1.0, False))
+    res = {"ms_one": one, "ms_four": four, "ratio": four / one}
     out["multi_rhs"] = res
     del A, xs, ys
 
@@ -181,7 +177,12 @@ if "stencil" in what:
     S = vx.stencil(ctx, np.full(width, 1.0 / width), width // 2)
     a, b = vx.vector(ctx, n), vx.vector(ctx, n)
     a.assign(vx.ElementIndex() * (1.0 / n) + 0.5)
-    ms = timeit(lambda: S.apply(a, b, 1.0, False))
-    out["stencil 2^26 w21"] = {"ms": ms, "gbs_compulsory": 16 * n / ms / 1e6, "frac": 16 * n / ms / 1e6 / PEAK}
+    res = {}
+    for k, nm in ((1, "one block per tile"), (0, "pipelined persistent blocks")):
+        vx.set_param("stencil.kernel", k)
+        ms = timeit(lambda: S.apply(a, b, 1.0, False))
+        res[nm] = {"ms": ms, "gbs_compulsory": 16 * n / ms / 1e6, "frac": 16 * n / ms / 1e6 / PEAK}
+    vx.set_param("stencil.kernel", 1)
+    out["stencil 2^26 w21"] = res
 
 print(json.dumps(out, indent=1))

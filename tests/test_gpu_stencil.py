@@ -58,3 +58,26 @@ def test_stencil_argument_checks(ctx1):
         vx.stencil(ctx1, [1.0, 2.0], 2)
     with pytest.raises(ValueError):
         vx.stencil(ctx1, [], 0)
+
+
+@pytest.mark.parametrize("nparts", [1, 2])
+def test_pipelined_stencil_kernel_same_bits(ctx1, ctx2, nparts):
+    """stencil.kernel = 0: persistent blocks with the next window arriving by cp.async (csrc/stencil.cu).  Opt-in (measured
+    slower than one block per tile), but selectable, so it is checked: more tiles than resident blocks, ragged end, both
+    precisions, `=` and `+=`, one and two slices (halo buffers as cp.async sources)."""
+    ctx = {1: ctx1, 2: ctx2}[nparts]
+    vx.set_param("stencil.kernel", 0)
+    try:
+        for n, width, center, dt in ((3_000_017, 21, 10, np.float64), (2_500_003, 5, 0, np.float64), (2_400_001, 33, 32, np.float32)):
+            s = oracle.uniform_real(width, width).astype(dt)
+            xh = oracle.uniform_real(n % 97 + 1, n).astype(dt)
+            S = vx.stencil(ctx, s, center, dtype=dt)
+            x, y = vx.vector(ctx, xh), vx.vector(ctx, n, dtype=dt)
+            want = ost.convolve(s, center, xh)
+            y.assign(x * S)
+            assert np.array_equal(y.read(), want)
+            y.assign(1.0)
+            y += S * x
+            assert np.array_equal(y.read(), (dt(1.0) + want).astype(dt))
+    finally:
+        vx.set_param("stencil.kernel", 1)

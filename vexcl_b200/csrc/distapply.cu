@@ -426,7 +426,7 @@ static int launch_dist(const vexb_dspmat *A, cudaStream_t st, const DistArgs<T> 
 #define DL(W) do { if (hell && S->ell_col16) dist_apply_kernel<T, W, short, DOT><<<grid, 256, 0, st>>>(a); \
                    else dist_apply_kernel<T, W, int, DOT><<<grid, 256, 0, st>>>(a); } while (0)
     switch (w) {
-        case 5: DL(5); break; case 7: DL(7); break; case 3: DL(3); break; case 9: DL(9); break;
+        case 5: DL(5); break; case 7: DL(7); break; case 3: DL(3); break; case 9: DL(9); break;   // = ell_width_is_unrolled_everywhere
         default: DL(0); break;
     }
 #undef DL

@@ -9,6 +9,10 @@ namespace vexb {
 // past the last entry share it.
 constexpr int kEllShiftSlots = 16;
 struct EllShifts { int s[kEllShiftSlots]; };
+// Widths for which EVERY kernel that walks an ELL strip has an unrolled instantiation (hell_kernel, hell_multi_kernel,
+// dist_apply_kernel: keep their switches in step with this).  Only those strips get one shift per slot: the kernels'
+// run-time loop over the slots reads shift.s[0] for all of them (indexing the by-value table at run time spills it).
+constexpr bool ell_width_is_unrolled_everywhere(size_t w) { return w == 3 || w == 5 || w == 7 || w == 9; }
 }
 
 struct vexb_spmat {

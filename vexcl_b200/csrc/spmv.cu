@@ -498,8 +498,7 @@ template <class T, int W, class C, int K>
 __global__ void __launch_bounds__(256) hell_multi_kernel(size_t n, size_t pitch, int w_dyn, const C *__restrict__ ell_col, const EllShifts shift,
                                                           const T *__restrict__ ell_val, const int *__restrict__ tail_ptr,
                                                           const int *__restrict__ tail_col, const T *__restrict__ tail_val,
-                                                          MultiPtr<K> mp, T alpha, int append, const int *__restrict__ row_ids, size_t y_offset,
-                                                          int flags) {
+                                                          MultiPtr<K> mp, T alpha, int append, const int *__restrict__ row_ids, size_t y_offset) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
@@ -512,13 +511,14 @@ __global__ void __launch_bounds__(256) hell_multi_kernel(size_t n, size_t pitch,
         for (int j = 0; j < W; ++j) { c[j] = ell_column(ldg_stream(ell_col + i + (size_t)j * pitch, stream), i, ell_shift_of(shift, j)); v[j] = ldg_stream(ell_val + i + (size_t)j * pitch, stream); }
         // one component at a time (W gathers in flight, then that component's products).  Issuing all K*W gathers first
         // was measured slower, with the default register budget (0.215 ms) as well as with 64 registers (0.213 ms),
-        // against 0.197 ms for this order at K = 4 on configs[2]
+        // against 0.197 ms for this order at K = 4 on configs[2]; plain loads of x instead of the L2 evict-last hint and
+        // streaming stores of y change nothing (profiles/r02_probe_window.json)
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const T *x = static_cast<const T *>(mp.x[k]);
             T xv[W > 0 ? W : 1];
 #pragma unroll
-            for (int j = 0; j < W; ++j) xv[j] = (c[j] != -1) ? ((flags & 1) ? __ldg(x + c[j]) : ldg_keep(x + c[j], keep)) : T(0);
+            for (int j = 0; j < W; ++j) xv[j] = (c[j] != -1) ? ldg_keep(x + c[j], keep) : T(0);
 #pragma unroll
             for (int j = 0; j < W; ++j) if (c[j] != -1) sum[k] = t_add<T>(sum[k], t_mul<T>(v[j], xv[j]));
         }
@@ -541,11 +541,7 @@ __global__ void __launch_bounds__(256) hell_multi_kernel(size_t n, size_t pitch,
     }
     const size_t r = row_ids ? (size_t)row_ids[i] : i + y_offset;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        T *y = static_cast<T *>(mp.y[k]);
-        if (flags & 2) { const T v = t_mul<T>(alpha, sum[k]); __stcs(y + r, append ? t_add<T>(y[r], v) : v); }
-        else store_y<T>(y, r, sum[k], alpha, append);
-    }
+    for (int k = 0; k < K; ++k) store_y<T>(static_cast<T *>(mp.y[k]), r, sum[k], alpha, append);
 }
 
 // spmv.kernel = 3: one thread per row straight from the CSR arrays ("CSR-scalar").  Neighbouring lanes read
@@ -1072,10 +1068,10 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
             // remaining slots.  spmv.col16 = 0 keeps 32-bit columns.
             std::vector<long long> lo(kEllShiftSlots, 0), hi(kEllShiftSlots, 0);
             std::vector<char> any(kEllShiftSlots, 0);
-            // Widths above 9 run the kernels' run-time loop over the slots, which cannot index the by-value shift table
-            // without spilling it to local memory (measured: 0.33 instead of 0.19 ms on a width-21 strip): such strips
-            // use ONE shift for all slots, as in round 1 (g = 0 for every slot).
-            const bool per_slot = w <= 9;
+            // Widths without an unrolled instantiation in every kernel run the kernels' run-time loop over the slots, which
+            // cannot index the by-value shift table without spilling it to local memory (measured: 0.33 instead of 0.19
+            // ms on a width-21 strip): such strips use ONE shift for all slots, as in round 1 (g = 0 for every slot).
+            const bool per_slot = ell_width_is_unrolled_everywhere(w);
             for (size_t k = 0; k < w; ++k) {
                 const size_t g = per_slot ? std::min<size_t>(k, kEllShiftSlots - 1) : 0;
                 for (size_t i = 0; i < n; ++i) {
@@ -1244,14 +1240,13 @@ static int spmv_multi_launch(const vexb_spmat *A, cudaStream_t st, const void *c
     MultiPtr<K> mp;
     for (int k = 0; k < K; ++k) { mp.x[k] = x[k]; mp.y[k] = y[k]; }
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    const int mflags = (int)param("spmv.multi_flags", 0);   // 1: gathers of x without the L2 evict-last hint, 2: streaming stores of y
 #define HM(W) do { \
         if (A->ell_col16) hell_multi_kernel<T, W, short, K><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col16, A->ell_shifts, \
-              (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, mp, alpha, append, A->row_ids, A->y_offset, mflags); \
+              (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, mp, alpha, append, A->row_ids, A->y_offset); \
         else hell_multi_kernel<T, W, int, K><<<blocks, 256, 0, st>>>(n, A->ell_pitch, (int)A->ell_width, A->ell_col, EllShifts{}, \
-              (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, mp, alpha, append, A->row_ids, A->y_offset, mflags); } while (0)
+              (const T *)A->ell_val, A->tail_ptr, A->tail_col, (const T *)A->tail_val, mp, alpha, append, A->row_ids, A->y_offset); } while (0)
     switch (A->ell_width) {
-        case 3: HM(3); break; case 5: HM(5); break; case 7: HM(7); break;
+        case 3: HM(3); break; case 5: HM(5); break; case 7: HM(7); break; case 9: HM(9); break;   // = ell_width_is_unrolled_everywhere
         default: HM(0); break;
     }
 #undef HM

@@ -229,10 +229,11 @@ static int stencil_launch(int dev, cudaStream_t st, const T *s, int width, int c
     }
     const unsigned blocks = (unsigned)((n + ST_B - 1) / ST_B);
     const int vec_io = aligned32(y) ? 1 : 0;
-    // stencil.kernel: 0 = pipelined persistent blocks (default when there are more tiles than resident blocks and two
-    // windows fit), 1 = one block per tile
+    // stencil.kernel: 1 = one block per tile (default), 0 = pipelined persistent blocks.  Measured at width 21, N = 2^26:
+    // 0.275 ms one-shot against 0.302 ms pipelined -- 8-byte cp.async copies into the padded layout cost more issue
+    // slots than the overlap across the 7 resident blocks of an SM already gives (profiles/r02_probe_stencil.json)
     const size_t smem2 = (2 * ((size_t)st_pad(wlen) + 1) + st_ceil8(width)) * sizeof(T);
-    if (param("stencil.kernel", 0) == 0 && smem2 <= 100 * 1024) {
+    if (param("stencil.kernel", 1) == 0 && smem2 <= 100 * 1024) {
         static std::atomic<unsigned long long> attr2[2];
         if (smem2 > 48 * 1024 && !(attr2[ti].load() & bit)) {
             VEXB_CUDA(cudaFuncSetAttribute(stencil_pipe_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
