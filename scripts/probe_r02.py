@@ -137,6 +137,23 @@ if "p3d" in what:
     out["poisson3d 256^3 hell"] = res
     del x, y
 
+if "small" in what:
+    # one GPU's share of the strong-scaled configs at N = 8, WITHOUT a halo: what the product costs when nothing is exchanged
+    res = {}
+    for label, dim, dims in (("configs[2]/8: 3162 x 396", 2, (3162, 396, None)), ("configs[3]/8: 256 x 256 x 32", 3, (256, 256, 32))):
+        row, col, val = gen.poisson_strip(dim, *[d for d in dims if d is not None])
+        N = row.size - 1
+        A = vx.SpMat(ctx, N, N, row, col, val, vx.FMT_AUTO)
+        x, y = vx.vector(ctx, N), vx.vector(ctx, N)
+        x.assign(vx.ElementIndex() * (1.0 / N) + 0.5)
+        ms = timeit(lambda: A.apply(x, y, 1.0, False), steps=200, warm=20)
+        from vexcl_b200.api import Graph
+        g = Graph(ctx, lambda: [A.apply(x, y, 1.0, False) for _ in range(10)])
+        msg = timeit(g.launch, steps=40, warm=5) / 10
+        res[label] = {"rows": N, "us_stream": ms * 1e3, "us_graph_of_10": msg * 1e3, "format_mb": int(A.info().loc.device_bytes) / 1e6}
+        del g, A, x, y
+    out["one eighth of the strong configs, no halo"] = res
+
 if "ccsr" in what:
     n = 256
     N = n ** 3
