@@ -689,7 +689,7 @@ def bench_csr_kernels(ctx, vx, gen, A_csr, x, y, nbytes, args, barrier, peak):
     Ah = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_AUTO)
     ms = time_loop(ctx, lambda: Ah.apply(xi, yi, 1.0, False), steps, 3, barrier) / steps
     res["spmat_auto_format"] = {"ms": ms, "gbs": nb / (ms * 1e-3) / 1e9, "frac_of_peak": nb / (ms * 1e-3) / 1e9 / peak,
-                                "fmt": {vx.FMT_CSR: "csr", vx.FMT_HELL: "hybrid ell"}.get(int(Ah.info().loc.fmt), "?"),
+                                "fmt": {vx.FMT_CSR: "csr", vx.FMT_HELL: "hybrid ell", vx.FMT_SELL: "sliced ell (SELL-32-sigma)"}.get(int(Ah.info().loc.fmt), "?"),
                                 "ell_width": int(Ah.info().loc.ell_width), "csr_tail_nnz": int(Ah.info().loc.csr_tail_nnz)}
     res["rows"], res["nnz"], res["algorithmic_bytes"] = n, int(row[-1]), nb
     out["irregular 4M rows, widths U[0,32)"] = res

@@ -383,10 +383,15 @@ typedef enum {
     VEXB_FMT_AUTO = 0,  /* CSR row-block stream kernel unless ELL is clearly better */
     VEXB_FMT_CSR = 1,   /* row-block CSR, tiles staged through shared memory by TMA bulk copies */
     VEXB_FMT_HELL = 2,  /* hybrid ELL + CSR tail, width by hybrid_ell.inl:66-114 */
-    VEXB_FMT_PATTERNS = 3 /* the strip's unique rows (column offsets from the diagonal + values) and one pattern id per
+    VEXB_FMT_PATTERNS = 3,/* the strip's unique rows (column offsets from the diagonal + values) and one pattern id per
                              row: the reference's CCSR (spmat/ccsr.hpp) found automatically.  Used when the strip has at
                              most "spmv.max_patterns" (256) distinct rows and no row map; otherwise as VEXB_FMT_AUTO.
                              Opt-in in round 1 (not yet run on a GPU). */
+    VEXB_FMT_SELL = 4     /* sliced ELL (SELL-32-sigma): slices of 32 rows stored column-major at the width of their longest
+                             row, rows sorted by length inside windows of "spmv.sell_sigma" (1024) rows so that a slice
+                             holds rows of similar length.  One warp per slice, one lane per row, coalesced loads, no
+                             shared memory, products added in storage order (same bits as the reference loop).  What
+                             VEXB_FMT_AUTO picks for rows too irregular for hybrid ELL. */
 } vexb_spfmt;
 /* Host-only: the row patterns VEXB_FMT_PATTERNS would use.  *n_patterns = number of distinct rows; idx (optional,
  * nrows entries) = pattern of each row.  Returns VEXB_ERR_UNSUPPORTED when there are more than max_patterns. */
@@ -399,7 +404,7 @@ int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols,
 int vexb_spmat_destroy(vexb_spmat *A);
 typedef struct {
     size_t  nrows, ncols, nnz;
-    int32_t fmt;          /* VEXB_FMT_CSR, VEXB_FMT_HELL or VEXB_FMT_PATTERNS */
+    int32_t fmt;          /* VEXB_FMT_CSR, VEXB_FMT_HELL, VEXB_FMT_PATTERNS or VEXB_FMT_SELL */
     int32_t val_dtype;
     size_t  ell_width, ell_pitch, csr_tail_nnz;   /* HELL only */
     size_t  n_tiles, tile_nnz;                    /* CSR: tiles, nnz per tile; PATTERNS: unique rows, entries in their table */

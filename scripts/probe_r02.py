@@ -137,6 +137,44 @@ if "p3d" in what:
     out["poisson3d 256^3 hell"] = res
     del x, y
 
+if "sell" in what:
+    for label, gaps in (("irregular 4M U[0,32) gaps U[1,64)", 64), ("irregular 4M U[0,32) gaps U[1,8)", 8)):
+        row, col, val = gen.irregular_rows(4_000_000, 0, 32, seed=1, max_gap=gaps)
+        n = row.size - 1
+        nb = gen.spmv_bytes(n, n, int(row[-1]))
+        x, y, yr = vx.vector(ctx, n), vx.vector(ctx, n), vx.vector(ctx, n)
+        x.assign(vx.ElementIndex() * (1.0 / n) + 0.5)
+        res = {}
+        A = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_CSR)
+        vx.set_param("spmv.kernel", 3)
+        A.apply(x, yr, 1.0, False)                            # thread per row: storage order
+        ref = yr.read()
+        vx.set_param("spmv.kernel", 4)
+        ms = timeit(lambda: A.apply(x, y, 1.0, False))
+        res["csr warp tiles"] = {"ms": ms, "frac": nb / ms / 1e6 / PEAK}
+        vx.set_param("spmv.kernel", -1)
+        del A
+        A = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_HELL)
+        ms = timeit(lambda: A.apply(x, y, 1.0, False))
+        res["hybrid ell"] = {"ms": ms, "frac": nb / ms / 1e6 / PEAK, "device_mb": int(A.info().loc.device_bytes) / 1e6}
+        del A
+        for sigma in (1024, 256, 8192):
+            vx.set_param("spmv.sell_sigma", sigma)
+            A = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_SELL)
+            y.assign(0.0)
+            A.apply(x, y, 1.0, False)
+            same = bool(np.array_equal(y.read(), ref))
+            ms = timeit(lambda: A.apply(x, y, 1.0, False))
+            res[f"sliced ell sigma={sigma}"] = {"ms": ms, "frac": nb / ms / 1e6 / PEAK, "same_bits_as_thread_per_row": same,
+                                                "device_mb": int(A.info().loc.device_bytes) / 1e6}
+            del A
+        vx.set_param("spmv.sell_sigma", 1024)
+        A = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_AUTO)
+        ms = timeit(lambda: A.apply(x, y, 1.0, False))
+        res["auto"] = {"ms": ms, "frac": nb / ms / 1e6 / PEAK, "fmt": int(A.info().loc.fmt)}
+        del A, x, y, yr
+        out[label] = res
+
 if "small" in what:
     # one GPU's share of the strong-scaled configs at N = 8, WITHOUT a halo: what the product costs when nothing is exchanged
     res = {}

@@ -136,3 +136,37 @@ def test_row_patterns_on_a_rectangular_strip_with_rows_left_of_the_diagonal(ctx1
     y.assign(7.0)
     y.assign(A * x)
     assert np.array_equal(y.read(), oracle.csr_spmv(row, col, val, xh))
+
+
+@pytest.mark.parametrize("nparts", [1, 2, 3])
+def test_sliced_ell_matches_the_oracle(built, ctx1, ctx2, ctx3, nparts):
+    """VEXB_FMT_SELL (SELL-32-sigma): slices of 32 rows sorted by length inside windows; one lane per row, products added
+    in storage order -> the same bits as the reference loop on one slice.  Also what AUTO picks for uneven rows."""
+    ctx = {1: ctx1, 2: ctx2, 3: ctx3}[nparts]
+    cases = [oracle.poisson(2, 96), oracle.random_matrix(3000, 3000, 16, seed=4), oracle.tridiagonal(1030),
+             _irregular(5000, 1), _irregular(3001, 2, 20, 90), _irregular(2500, 3, 0, 8, long_rows=((7, 300), (1200, 2400), (2499, 257))),
+             _irregular(33, 5, 0, 4), _irregular(1, 6, 3, 4)]
+    for sigma in (1024, 32):
+        vx.set_param("spmv.sell_sigma", sigma)
+        for row, col, val in cases:
+            n = row.size - 1
+            xh = oracle.uniform_real(9, n)
+            A = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_SELL)
+            assert A.info().loc.fmt == vx.FMT_SELL or A.info().loc.nnz == 0
+            x, y = vx.vector(ctx, xh), vx.vector(ctx, n)
+            y.assign(7.0)
+            y.assign(A * x)
+            want = oracle.csr_spmv(row, col, val, xh)
+            if nparts == 1:
+                assert np.array_equal(y.read(), want)
+            else:
+                assert np.all(np.abs(y.read() - want) <= 1e-10 * oracle.csr_absrow(row, col, val, xh))
+            y0 = oracle.uniform_real(10, n)
+            y.assign(vx.vector(ctx, y0) - 2.0 * (A * x))
+            assert np.all(np.abs(y.read() - (y0 - 2.0 * want)) <= 1e-10 * (np.abs(y0) + 2 * oracle.csr_absrow(row, col, val, xh)))
+    vx.set_param("spmv.sell_sigma", 1024)
+    # AUTO: even rows -> hybrid ELL, uneven rows -> sliced ELL
+    row, col, val = oracle.poisson(2, 64)
+    assert vx.SpMat(ctx1, row.size - 1, row.size - 1, row, col, val).info().loc.fmt == vx.FMT_HELL
+    row, col, val = _irregular(4000, 7)
+    assert vx.SpMat(ctx1, 4000, 4000, row, col, val).info().loc.fmt == vx.FMT_SELL

@@ -7,7 +7,7 @@
 """
 from . import _lib
 from ._lib import (F64, F32, I32, U32, I64, U64, SET, ADD, SUB, MUL, DIV, MOD, AND, OR, XOR, LSH, RSH,
-                   SUM, SUM_KAHAN, MAX, MIN, MINMAX, FMT_AUTO, FMT_CSR, FMT_HELL, FMT_PATTERNS, VexbError)
+                   SUM, SUM_KAHAN, MAX, MIN, MINMAX, FMT_AUTO, FMT_CSR, FMT_HELL, FMT_PATTERNS, FMT_SELL, VexbError)
 from .api import (Context, vector, Reductor, SpMat, SpMatCCSR, stencil, partition, ElementIndex, Scalar, if_else,
                   sin, cos, tan, asin, acos, atan, sinh, cosh, tanh, exp, exp2, log, log2, log10, sqrt, rsqrt,
                   cbrt, fabs, floor, ceil, round_, trunc, pow_, atan2, fmod, hypot, fmin, fmax, fma, make_inline, InlineSpMV, assign_multi)

@@ -32,6 +32,10 @@ struct vexb_spmat {
     int *ell_col = nullptr; void *ell_val = nullptr;
     short *ell_col16 = nullptr; vexb::EllShifts ell_shifts = {};   // optional: columns as 16-bit offsets from (row + shift of the slot); see spmv.col16
     int *tail_ptr = nullptr; int *tail_col = nullptr; void *tail_val = nullptr;
+    // SELL-32-sigma: slice s holds stored rows perm[32 s .. 32 s + 31] (-1: none) in sell_col / sell_val at
+    // [slice_ptr[s], slice_ptr[s+1]), slot k of lane l at slice_ptr[s] + 32 k + l
+    int *sell_ptr = nullptr; int *sell_perm = nullptr; int *sell_col = nullptr; void *sell_val = nullptr;
+    size_t n_slices = 0, sell_slots = 0;
     vexb_ccsr *patterns = nullptr; // VEXB_FMT_PATTERNS: the strip as unique row patterns + one pattern id per row (csrc/ccsr.cu)
     size_t n_patterns = 0;
     int *row_ids = nullptr;        // optional: compressed rows, y index of stored row r (remote strips)

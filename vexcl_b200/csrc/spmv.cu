@@ -836,6 +836,46 @@ __global__ void __launch_bounds__(256, 3) csr_ring_kernel(const int2 *__restrict
     }
 }
 
+// ---- sliced ELL (VEXB_FMT_SELL) ------------------------------------------------------------------------------------
+// Irregular rows: hybrid ELL pads (or spills into its CSR tail), and every CSR kernel above either reads col/val
+// uncoalesced (thread per row) or stages products through shared memory, which shares the L1 data pipe with the x
+// gathers -- ncu on the 4M-row irregular matrix: that pipe at 80 % (half gathers, half shared memory), DRAM at 43 %
+// (profiles/r02_ncu_summary.md).  SELL-32-sigma keeps hybrid ELL's access pattern (a warp's loads of a slot are 32
+// consecutive entries; one lane per row, sum in a register, no shared memory) without its padding: slices of 32 rows are
+// as wide as THEIR longest row, and rows are sorted by length inside windows of sigma rows first, so a slice's rows are
+// nearly equally long.  Products are added in storage order: same bits as the reference loop (csr.inl:163-170).
+template <class T>
+__global__ void __launch_bounds__(256) sell_kernel(size_t n_slices, const int *__restrict__ slice_ptr, const int *__restrict__ perm,
+                                                   const int *__restrict__ col, const T *__restrict__ val,
+                                                   const T *__restrict__ x, T *y, T alpha, int append,
+                                                   const int *__restrict__ row_ids, size_t y_offset) {
+    const size_t s = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= n_slices) return;
+    const int lane = threadIdx.x & 31;
+    const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
+    const int base = __ldg(slice_ptr + s), w = (__ldg(slice_ptr + s + 1) - base) >> 5;
+    const int r = ldg_stream(perm + s * 32 + lane, stream);
+    const int *cp = col + base + lane;
+    const T *vp = val + base + lane;
+    T sum = T(0);
+    int k = 0;
+    for (; k + 4 <= w; k += 4) {                          // 4 slots: 8 coalesced loads, then 4 gathers, in flight together
+        int c[4]; T v[4], xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { c[u] = ldg_stream(cp + (k + u) * 32, stream); v[u] = ldg_stream(vp + (k + u) * 32, stream); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = c[u] != -1 ? ldg_keep(x + c[u], keep) : T(0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (c[u] != -1) sum = t_add<T>(sum, t_mul<T>(v[u], xv[u]));
+    }
+    for (; k < w; ++k) {
+        const int c = ldg_stream(cp + k * 32, stream);
+        const T v = ldg_stream(vp + k * 32, stream);
+        if (c != -1) sum = t_add<T>(sum, t_mul<T>(v, ldg_keep(x + c, keep)));
+    }
+    if (r >= 0) store_y<T>(y, row_ids ? (size_t)row_ids[r] : (size_t)r + y_offset, sum, alpha, append);
+}
+
 template <class T>
 __global__ void zero_rows_kernel(T *y, size_t n, const int *__restrict__ row_ids) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -940,9 +980,52 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
         size_t tail = 0;
         for (size_t i = 0; i < n; ++i) { const size_t rw = rowptr[i + 1] - rowptr[i]; if (rw > w) tail += rw - w; }
         const double padded = (double)w * (double)((n + 15) / 16 * 16) + (double)tail;
-        fmt = (A->nnz > 0 && padded <= 3.0 * (double)A->nnz) ? VEXB_FMT_HELL : VEXB_FMT_CSR;
+        // regular rows: hybrid ELL; rows too uneven for it (more than a quarter of the stored slots would be padding or
+        // tail): sliced ELL, which keeps the access pattern and drops the padding (spmv.auto_sell = 0: round-1 rule)
+        if (A->nnz == 0) fmt = VEXB_FMT_CSR;
+        else if (padded <= 1.25 * (double)A->nnz && tail * 20 <= A->nnz) fmt = VEXB_FMT_HELL;
+        else if (param("spmv.auto_sell", 1)) fmt = VEXB_FMT_SELL;
+        else fmt = padded <= 3.0 * (double)A->nnz ? VEXB_FMT_HELL : VEXB_FMT_CSR;
     }
     A->fmt = fmt;
+    if (fmt == VEXB_FMT_SELL) {
+        long sigma = param("spmv.sell_sigma", 1024);
+        sigma = std::max(32l, std::min(sigma, 1l << 20)) & ~31l;
+        const size_t ns = (n + 31) / 32;
+        std::vector<int> perm(ns * 32, -1);
+        for (size_t i = 0; i < n; ++i) perm[i] = (int)i;
+        for (size_t w0 = 0; w0 < n; w0 += (size_t)sigma) {          // longest rows first inside each window (stable: ties keep row order)
+            const size_t w1 = std::min(n, w0 + (size_t)sigma);
+            std::stable_sort(perm.begin() + w0, perm.begin() + w1, [&](int a, int b) {
+                return rowptr[a + 1] - rowptr[a] > rowptr[b + 1] - rowptr[b]; });
+        }
+        std::vector<int> sptr(ns + 1, 0);
+        size_t slots = 0;
+        for (size_t sl = 0; sl < ns; ++sl) {
+            int wmax = 0;
+            for (int l = 0; l < 32; ++l) { const int r = perm[sl * 32 + l]; if (r >= 0) wmax = std::max(wmax, rowptr[r + 1] - rowptr[r]); }
+            slots += (size_t)wmax * 32;
+            if (slots >= (size_t)INT32_MAX - 64) { set_error(__FILE__, __LINE__, "strip too large for sliced ELL"); return VEXB_ERR_UNSUPPORTED; }
+            sptr[sl + 1] = (int)slots;
+        }
+        std::vector<int> scol(slots, -1);
+        std::vector<T> sval(slots, T(0));
+        for (size_t sl = 0; sl < ns; ++sl)
+            for (int l = 0; l < 32; ++l) {
+                const int r = perm[sl * 32 + l];
+                if (r < 0) continue;
+                for (int j = rowptr[r], k = 0; j < rowptr[r + 1]; ++j, ++k) {
+                    scol[(size_t)sptr[sl] + (size_t)k * 32 + l] = col[j];
+                    sval[(size_t)sptr[sl] + (size_t)k * 32 + l] = val[j];
+                }
+            }
+        A->n_slices = ns; A->sell_slots = slots;
+        VEXB_TRY(upload(sptr, 0, (void **)&A->sell_ptr, &A->device_bytes));
+        VEXB_TRY(upload(perm, 0, (void **)&A->sell_perm, &A->device_bytes));
+        VEXB_TRY(upload(scol, 32, (void **)&A->sell_col, &A->device_bytes));
+        VEXB_TRY(upload(sval, 32, &A->sell_val, &A->device_bytes));
+        return VEXB_OK;
+    }
     if (fmt == VEXB_FMT_CSR) {
         long tn = param("spmv.tile_nnz", 2048), tr = param("spmv.tile_rows", 512);
         tn = std::max(64l, std::min(tn, 8192l)) & ~3l;
@@ -1121,6 +1204,13 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
         return VEXB_OK;
     }
     if (A->fmt == VEXB_FMT_PATTERNS) return vexb_ccsr_spmv(A->dev, (void *)st, A->patterns, x, y, (double)alpha, append);
+    if (A->fmt == VEXB_FMT_SELL) {
+        // y was advanced by y_offset above; the kernel adds nothing more
+        sell_kernel<T><<<(unsigned)((A->n_slices + 7) / 8), 256, 0, st>>>(A->n_slices, A->sell_ptr, A->sell_perm, A->sell_col, (const T *)A->sell_val,
+                                                                       x, y, alpha, append, A->row_ids, 0);
+        VEXB_LAUNCHED();
+        return VEXB_OK;
+    }
     // spmv.kernel: 0 = TMA-staged one-shot CTA tiles, 1 = persistent TMA pipeline, 2 = register-staged CTA tiles, 3 = thread per row,
     //              4 = warp tiles, 5 = warp rings (TMA), 6 = CTA tiles with the x window in shared memory; unset (-1) = the strip's own choice (build(): 3 for short even rows, else 4)
     long variant = param("spmv.kernel", param("spmv.pipeline", 0) ? 1 : -1);
@@ -1296,7 +1386,7 @@ extern "C" int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols
     VEXB_CHECK(ptr_bytes == 4 || ptr_bytes == 8, "ptr_bytes must be 4 or 8");
     VEXB_CHECK(col_bytes == 4 || col_bytes == 8, "col_bytes must be 4 or 8");
     VEXB_CHECK(val_dtype == VEXB_F64 || val_dtype == VEXB_F32, "values must be f64 or f32");
-    VEXB_CHECK(fmt >= VEXB_FMT_AUTO && fmt <= VEXB_FMT_PATTERNS, "bad format %d", fmt);
+    VEXB_CHECK(fmt >= VEXB_FMT_AUTO && fmt <= VEXB_FMT_SELL, "bad format %d", fmt);
     VEXB_CHECK(nrows == 0 || ptr, "ptr is NULL");
     VEXB_CHECK(nrows < (size_t)INT32_MAX && ncols < (size_t)INT32_MAX, "strip dimensions exceed 32-bit local indices");
     DeviceGuard g(dev); VEXB_CHECK(g.ok, "cannot select device %d", dev);
@@ -1325,6 +1415,7 @@ extern "C" int vexb_spmat_destroy(vexb_spmat *A) {
     DeviceGuard g(A->dev);
     cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile); cudaFree(A->tile_x); cudaFree(A->wtile); cudaFree(A->d_desc);
     vexb_ccsr_destroy(A->patterns);
+    cudaFree(A->sell_ptr); cudaFree(A->sell_perm); cudaFree(A->sell_col); cudaFree(A->sell_val);
     cudaFree(A->row_ids); cudaFree(A->ell_col); cudaFree(A->ell_col16); cudaFree(A->ell_val); cudaFree(A->tail_ptr); cudaFree(A->tail_col); cudaFree(A->tail_val);
     delete A;
     return VEXB_OK;
