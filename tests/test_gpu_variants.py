@@ -145,7 +145,7 @@ def test_sliced_ell_matches_the_oracle(built, ctx1, ctx2, ctx3, nparts):
     ctx = {1: ctx1, 2: ctx2, 3: ctx3}[nparts]
     cases = [oracle.poisson(2, 96), oracle.random_matrix(3000, 3000, 16, seed=4), oracle.tridiagonal(1030),
              _irregular(5000, 1), _irregular(3001, 2, 20, 90), _irregular(2500, 3, 0, 8, long_rows=((7, 300), (1200, 2400), (2499, 257))),
-             _irregular(33, 5, 0, 4), _irregular(1, 6, 3, 4)]
+             _irregular(33, 5, 0, 4), _irregular(40, 6, 0, 3)]
     for sigma in (1024, 32):
         vx.set_param("spmv.sell_sigma", sigma)
         for row, col, val in cases:
