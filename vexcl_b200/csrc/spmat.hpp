@@ -35,6 +35,7 @@ struct vexb_spmat {
     // SELL-32-sigma: slice s holds stored rows perm[32 s .. 32 s + 31] (-1: none) in sell_col / sell_val at
     // [slice_ptr[s], slice_ptr[s+1]), slot k of lane l at slice_ptr[s] + 32 k + l
     int *sell_ptr = nullptr; int *sell_perm = nullptr; int *sell_col = nullptr; void *sell_val = nullptr;
+    short *sell_col16 = nullptr; int sell_shift = 0;   // optional 16-bit columns: distance from (row + sell_shift), -32768 = padding
     size_t n_slices = 0, sell_slots = 0;
     vexb_ccsr *patterns = nullptr; // VEXB_FMT_PATTERNS: the strip as unique row patterns + one pattern id per row (csrc/ccsr.cu)
     size_t n_patterns = 0;

@@ -844,9 +844,11 @@ __global__ void __launch_bounds__(256, 3) csr_ring_kernel(const int2 *__restrict
 // consecutive entries; one lane per row, sum in a register, no shared memory) without its padding: slices of 32 rows are
 // as wide as THEIR longest row, and rows are sorted by length inside windows of sigma rows first, so a slice's rows are
 // nearly equally long.  Products are added in storage order: same bits as the reference loop (csr.inl:163-170).
-template <class T>
+// C = short: a stored column is its distance from (the lane's row + shift), -32768 = padding (banded strips: 10 instead
+// of 12 bytes per slot); C = int: the column itself, -1 = padding.
+template <class T, class C>
 __global__ void __launch_bounds__(256) sell_kernel(size_t n_slices, const int *__restrict__ slice_ptr, const int *__restrict__ perm,
-                                                   const int *__restrict__ col, const T *__restrict__ val,
+                                                   const C *__restrict__ col, int shift, const T *__restrict__ val,
                                                    const T *__restrict__ x, T *y, T alpha, int append,
                                                    const int *__restrict__ row_ids, size_t y_offset) {
     const size_t s = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -855,21 +857,22 @@ __global__ void __launch_bounds__(256) sell_kernel(size_t n_slices, const int *_
     const uint64_t stream = l2_policy_stream(), keep = l2_policy_keep();
     const int base = __ldg(slice_ptr + s), w = (__ldg(slice_ptr + s + 1) - base) >> 5;
     const int r = ldg_stream(perm + s * 32 + lane, stream);
-    const int *cp = col + base + lane;
+    const C *cp = col + base + lane;
     const T *vp = val + base + lane;
+    const size_t rr = r >= 0 ? (size_t)r : 0;
     T sum = T(0);
     int k = 0;
     for (; k + 4 <= w; k += 4) {                          // 4 slots: 8 coalesced loads, then 4 gathers, in flight together
         int c[4]; T v[4], xv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { c[u] = ldg_stream(cp + (k + u) * 32, stream); v[u] = ldg_stream(vp + (k + u) * 32, stream); }
+        for (int u = 0; u < 4; ++u) { c[u] = ell_column(ldg_stream(cp + (k + u) * 32, stream), rr, shift); v[u] = ldg_stream(vp + (k + u) * 32, stream); }
 #pragma unroll
         for (int u = 0; u < 4; ++u) xv[u] = c[u] != -1 ? ldg_keep(x + c[u], keep) : T(0);
 #pragma unroll
         for (int u = 0; u < 4; ++u) if (c[u] != -1) sum = t_add<T>(sum, t_mul<T>(v[u], xv[u]));
     }
     for (; k < w; ++k) {
-        const int c = ldg_stream(cp + k * 32, stream);
+        const int c = ell_column(ldg_stream(cp + k * 32, stream), rr, shift);
         const T v = ldg_stream(vp + k * 32, stream);
         if (c != -1) sum = t_add<T>(sum, t_mul<T>(v, ldg_keep(x + c, keep)));
     }
@@ -1022,7 +1025,31 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
         A->n_slices = ns; A->sell_slots = slots;
         VEXB_TRY(upload(sptr, 0, (void **)&A->sell_ptr, &A->device_bytes));
         VEXB_TRY(upload(perm, 0, (void **)&A->sell_perm, &A->device_bytes));
-        VEXB_TRY(upload(scol, 32, (void **)&A->sell_col, &A->device_bytes));
+        bool narrow = false;
+        if (param("spmv.col16", 1) && A->nnz > 0) {
+            // banded strips: every column within +-32767 of (its row + one shift) -> 16-bit columns, as for hybrid ELL
+            long long lo = 0, hi = 0; bool any = false;
+            for (size_t i = 0; i < n; ++i)
+                for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+                    const long long d = (long long)col[j] - (long long)i;
+                    if (!any) { lo = hi = d; any = true; } else { lo = std::min(lo, d); hi = std::max(hi, d); }
+                }
+            if (any && hi - lo <= 65534) {
+                const long long shift = lo + 32767;
+                std::vector<short> s16(slots, (short)-32768);
+                for (size_t sl = 0; sl < ns; ++sl)
+                    for (int l = 0; l < 32; ++l) {
+                        const int r = perm[sl * 32 + l];
+                        if (r < 0) continue;
+                        for (int j = rowptr[r], k = 0; j < rowptr[r + 1]; ++j, ++k)
+                            s16[(size_t)sptr[sl] + (size_t)k * 32 + l] = (short)((long long)col[j] - (long long)r - shift);
+                    }
+                A->sell_shift = (int)shift;
+                VEXB_TRY(upload(s16, 32, (void **)&A->sell_col16, &A->device_bytes));
+                narrow = true;
+            }
+        }
+        if (!narrow) VEXB_TRY(upload(scol, 32, (void **)&A->sell_col, &A->device_bytes));
         VEXB_TRY(upload(sval, 32, &A->sell_val, &A->device_bytes));
         return VEXB_OK;
     }
@@ -1206,8 +1233,11 @@ static int spmv_launch(const vexb_spmat *A, cudaStream_t st, const T *x, T *y, T
     if (A->fmt == VEXB_FMT_PATTERNS) return vexb_ccsr_spmv(A->dev, (void *)st, A->patterns, x, y, (double)alpha, append);
     if (A->fmt == VEXB_FMT_SELL) {
         // y was advanced by y_offset above; the kernel adds nothing more
-        sell_kernel<T><<<(unsigned)((A->n_slices + 7) / 8), 256, 0, st>>>(A->n_slices, A->sell_ptr, A->sell_perm, A->sell_col, (const T *)A->sell_val,
-                                                                       x, y, alpha, append, A->row_ids, 0);
+        const unsigned sb = (unsigned)((A->n_slices + 7) / 8);
+        if (A->sell_col16) sell_kernel<T, short><<<sb, 256, 0, st>>>(A->n_slices, A->sell_ptr, A->sell_perm, A->sell_col16, A->sell_shift, (const T *)A->sell_val,
+                                                                   x, y, alpha, append, A->row_ids, 0);
+        else sell_kernel<T, int><<<sb, 256, 0, st>>>(A->n_slices, A->sell_ptr, A->sell_perm, A->sell_col, 0, (const T *)A->sell_val,
+                                                   x, y, alpha, append, A->row_ids, 0);
         VEXB_LAUNCHED();
         return VEXB_OK;
     }
@@ -1415,7 +1445,7 @@ extern "C" int vexb_spmat_destroy(vexb_spmat *A) {
     DeviceGuard g(A->dev);
     cudaFree(A->val); cudaFree(A->col); cudaFree(A->rowptr); cudaFree(A->tile); cudaFree(A->tile_x); cudaFree(A->wtile); cudaFree(A->d_desc);
     vexb_ccsr_destroy(A->patterns);
-    cudaFree(A->sell_ptr); cudaFree(A->sell_perm); cudaFree(A->sell_col); cudaFree(A->sell_val);
+    cudaFree(A->sell_ptr); cudaFree(A->sell_perm); cudaFree(A->sell_col); cudaFree(A->sell_col16); cudaFree(A->sell_val);
     cudaFree(A->row_ids); cudaFree(A->ell_col); cudaFree(A->ell_col16); cudaFree(A->ell_val); cudaFree(A->tail_ptr); cudaFree(A->tail_col); cudaFree(A->tail_val);
     delete A;
     return VEXB_OK;
