@@ -9,7 +9,7 @@ mkdir -p gpurun_out /tmp/ncu
 NCU="ncu --clock-control none"
 want() { [ $# -eq 0 ] || return 0; }
 TARGETS="${*:-launches hell csr_scalar csr_warp ccsr ccsr_jit stencil dist_apply cg_update interp hell_multi}"
-KEEP_REP="${KEEP_REP:-csr_warp stencil ccsr_jit}"
+KEEP_REP="${KEEP_REP:-sell stencil ccsr_jit}"
 has() { case " $TARGETS " in *" $1 "*) return 0;; esac; return 1; }
 if has launches; then
     timeout 500 $NCU --metrics gpu__time_duration.sum -c 1500 --csv --log-file gpurun_out/r02_launches_bench.csv \
@@ -41,5 +41,6 @@ cap dist_apply 'dist_apply_kernel' 1 cg
 cap cg_update 'cg_update' 2 cg
 cap interp '^interp_kernel' 1 vec
 cap hell_multi 'hell_multi_kernel' 2 hell multi_rhs
+cap sell 'sell_kernel' 2 sell
 if [ "$(du -sm gpurun_out | cut -f1)" -ge 60 ]; then rm -f gpurun_out/*.ncu-rep; echo "reports dropped to stay under the size limit"; fi
 du -sh gpurun_out

@@ -82,6 +82,17 @@ if "csr_irregular" in what:
     ctx.finish()
     del Ai, xi, yi
 
+if "sell" in what:
+    n = 4_000_000
+    row, col, val = gen.irregular_rows(n, 0, 32, seed=1)
+    xi, yi = vx.vector(ctx, n), vx.vector(ctx, n)
+    xi.assign(vx.ElementIndex() * (1.0 / n) + 0.5)
+    Ai = vx.SpMat(ctx, n, n, row, col, val, vx.FMT_AUTO)          # uneven rows: sliced ELL
+    for _ in range(REPS):
+        Ai.apply(xi, yi, 1.0, False)
+    ctx.finish()
+    del Ai, xi, yi
+
 if "ccsr" in what or "ccsr_jit" in what:
     n = 256
     N = n ** 3
