@@ -235,6 +235,8 @@ int vexb_function_register(const char *name, int ret_dtype, int nargs, const int
 /* Generated source and NVRTC build log of the kernel vexb_eval would JIT for this request (for inspection
  * and for tests on machines without a GPU: NVRTC needs no device).  Two-call pattern on *len. */
 int vexb_jit_source(int lhs_dtype, int assign_op, const vexb_expr *expr, char *buf, size_t *len, int compile);
+/* The same for the one kernel vexb_eval_multi generates for ncomp (2..8) components. */
+int vexb_jit_source_multi(int lhs_dtype, int assign_op, int ncomp, const vexb_expr *const *exprs, char *buf, size_t *len, int compile);
 /* Expressions without a hand-written sweep are served by the pre-compiled interpreter while NVRTC builds a kernel
  * specialised to the expression on a background thread (started at the first use of a new expression shape; tunable
  * "eval.jit": 0 = interpreter only, 1 = compile synchronously, 2 = this, the default).  *pending = 1 while any such
