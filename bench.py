@@ -443,7 +443,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     r0, r1 = int(part[k]), int(part[k + 1])
     row, col, val = gen.poisson_strip(2, nx, ny, r0=r0, r1=r1, index_dtype=np.int64)
     slab_rows, slab_nnz = r1 - r0, int(row[-1])
-    fmt = {"auto": vx.FMT_AUTO, "csr": vx.FMT_CSR, "hell": vx.FMT_HELL, "patterns": vx.FMT_PATTERNS}[args.format]
+    fmt = {"auto": vx.FMT_AUTO, "csr": vx.FMT_CSR, "hell": vx.FMT_HELL, "patterns": vx.FMT_PATTERNS, "sell": vx.FMT_SELL}[args.format]
     A = vx.SpMat(ctx, N, N, row, col, val, fmt, strip=True)
     info = A.info()
     A_alt = None
@@ -505,8 +505,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
     is_hell = loc.fmt == vx.FMT_HELL
     is_patterns = loc.fmt == vx.FMT_PATTERNS
+    is_sell = loc.fmt == vx.FMT_SELL
     kname = (f"hell_kernel<double,{int(loc.ell_width)}>" if is_hell else
-             f"ccsr_kernel<double> ({int(loc.n_tiles)} row patterns)" if is_patterns else "csr_stream_kernel<double>")
+             f"ccsr_kernel<double> ({int(loc.n_tiles)} row patterns)" if is_patterns else
+             "sell_kernel<double>" if is_sell else
+             "csr_scalar_kernel<double> (thread per row: the strip's own choice for short even rows)")
     traffic, traffic_note = load_traffic("hell_kernel" if is_hell else "ccsr_kernel" if is_patterns else "csr_kernel")
     # what the stored format must move at least: hybrid ELL has no row pointers, and its columns are 16-bit offsets from
     # the diagonal when the band allows (configs[2]); padding slots are read as columns only
@@ -645,7 +648,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                   f"{int(loc.ell_width)}, CSR tail {int(loc.csr_tail_nnz)} nnz, 32-bit columns" if is_hell else
                                   f"CSR in; device format: {int(loc.n_tiles)} unique row patterns + one pattern id per row "
                                   f"(VEXB_FMT_PATTERNS, requested explicitly)" if is_patterns else
-                                  f"CSR in; device format: CSR row-block stream (TMA-staged tiles of {int(loc.tile_nnz)} nnz), 32-bit indices"),
+                                  "CSR in; device format: sliced ELL (SELL-32-sigma)" if is_sell else
+                                  "CSR in; device format: CSR (32-bit indices), thread-per-row kernel"),
                        "requested_format": args.format,
                        "cache": "inputs larger than L2 (0.8 GB per GPU vs 126 MB L2)", "partition": "equal weights",
                        "reference_arm": "bench.py --impl reference always times the 10M-row configs[2] matrix on the host cores; at "
@@ -943,7 +947,7 @@ def main():
     ap.add_argument("--no-peer", action="store_true", help="combine reductions with ncclAllReduce instead of the fused peer-memory exchange")
     ap.add_argument("--no-peer-halo", action="store_true", help="exchange SpMat halos with NCCL send/recv instead of the in-kernel peer-memory push")
     ap.add_argument("--no-strong", action="store_true", help="skip extra.strong (the named configurations split over the N GPUs)")
-    ap.add_argument("--format", default="auto", choices=["auto", "csr", "hell", "patterns"])
+    ap.add_argument("--format", default="auto", choices=["auto", "csr", "hell", "patterns", "sell"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
