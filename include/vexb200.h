@@ -400,6 +400,11 @@ typedef enum {
 int vexb_csr_row_patterns(size_t nrows, const void *ptr, int ptr_bytes, const void *col, int col_bytes,
                           const void *val, int val_dtype, size_t max_patterns, size_t *n_patterns, int32_t *idx);
 
+/* Host-only: the sliced-ELL layout VEXB_FMT_SELL would use.  perm (optional, 32 * n_slices entries): the row each slice
+ * lane multiplies, -1 = none; slice_ptr (optional, n_slices + 1): first slot of each slice.  sigma = sorting window. */
+int vexb_csr_sell_layout(size_t nrows, const void *ptr, int ptr_bytes, long sigma, size_t *n_slices, size_t *n_slots,
+                         int32_t *perm, int32_t *slice_ptr);
+
 int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols,
                     const void *ptr, int ptr_bytes, const void *col, int col_bytes,
                     const void *val, int val_dtype, int fmt, vexb_spmat **out);

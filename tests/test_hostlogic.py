@@ -245,3 +245,41 @@ def test_product_never_uses_the_oracle():
                     if pat.search(line) and "build_oracle" not in line and "ORACLE_" not in line and p.name != "build.py":
                         offenders.append(f"{p.relative_to(ROOT)}:{ln}: {line.strip()}")
     assert not offenders, "\n".join(offenders)
+
+
+def test_sliced_ell_layout_host_only(built):
+    """VEXB_FMT_SELL (csrc/spmv.cu): windows of sigma rows sorted by length (longest first, ties in row order), slices of 32
+    lanes as wide as their longest row.  Host logic: checked here without a GPU against a numpy restatement."""
+    import ctypes as C
+    from vexcl_b200 import _lib as L
+    lib = L.lib()
+    rng = np.random.default_rng(11)
+    for n, sigma in ((5000, 1024), (1000, 32), (33, 64), (1, 32), (4096, 4096), (0, 1024)):
+        w = rng.integers(0, 32, n)
+        if n > 7:
+            w[7] = 300                                                  # one long row
+        row = np.concatenate([[0], np.cumsum(w)]).astype(np.int64)
+        ns, slots = C.c_size_t(0), C.c_size_t(0)
+        L.check(lib.vexb_csr_sell_layout(n, row.ctypes.data, 8, sigma, C.byref(ns), C.byref(slots), None, None))
+        assert ns.value == (n + 31) // 32
+        perm = np.full(ns.value * 32, -7, np.int32)
+        sptr = np.full(ns.value + 1, -7, np.int32)
+        L.check(lib.vexb_csr_sell_layout(n, row.ctypes.data, 8, sigma, C.byref(ns), C.byref(slots), perm.ctypes.data, sptr.ctypes.data))
+        # numpy restatement
+        want = np.full(ns.value * 32, -1, np.int64)
+        for w0 in range(0, n, sigma):
+            idx = np.arange(w0, min(n, w0 + sigma))
+            want[w0:w0 + idx.size] = idx[np.argsort(-w[idx], kind="stable")]
+        assert np.array_equal(perm, want)
+        assert sorted(perm[perm >= 0]) == list(range(n))                # a permutation of the rows
+        widths = np.array([max([w[r] for r in perm[s * 32:(s + 1) * 32] if r >= 0], default=0) for s in range(ns.value)], dtype=np.int64)
+        assert np.array_equal(sptr, np.concatenate([[0], np.cumsum(widths * 32)]))
+        assert slots.value == int(widths.sum() * 32)
+        if n == 5000:                                                   # sorting keeps the padding small: < 10 % on U[0,32) + one long row
+            assert slots.value <= 1.10 * row[-1] + 300 * 32
+    # 32-bit row pointers, decreasing pointers rejected
+    row32 = np.array([0, 3, 5, 9], np.int32)
+    L.check(lib.vexb_csr_sell_layout(3, row32.ctypes.data, 4, 32, C.byref(ns), C.byref(slots), None, None))
+    assert (ns.value, slots.value) == (1, 4 * 32)
+    bad = np.array([0, 3, 2], np.int64)
+    assert lib.vexb_csr_sell_layout(2, bad.ctypes.data, 8, 32, C.byref(ns), C.byref(slots), None, None) == 2

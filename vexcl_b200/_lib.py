@@ -146,6 +146,7 @@ def lib():
         "vexb_halo_plan_send_cols": ([vp, i, vp], i),
         "vexb_csr_create": ([i, vp, sz, sz, vp, i, vp, i, vp, i, i, P(vp)], i),
         "vexb_csr_row_patterns": ([sz, vp, i, vp, i, vp, i, sz, P(sz), vp], i),
+        "vexb_csr_sell_layout": ([sz, vp, i, C.c_long, P(sz), P(sz), vp, vp], i),
         "vexb_spmat_destroy": ([vp], i),
         "vexb_spmat_get_info": ([vp, P(SpmatInfo)], i),
         "vexb_spmat_hell_download": ([vp, vp, vp, vp, vp, vp], i),

@@ -992,25 +992,13 @@ static int build(vexb_spmat *A, std::vector<int> &rowptr, std::vector<int> &col,
     }
     A->fmt = fmt;
     if (fmt == VEXB_FMT_SELL) {
-        long sigma = param("spmv.sell_sigma", 1024);
-        sigma = std::max(32l, std::min(sigma, 1l << 20)) & ~31l;
-        const size_t ns = (n + 31) / 32;
-        std::vector<int> perm(ns * 32, -1);
-        for (size_t i = 0; i < n; ++i) perm[i] = (int)i;
-        for (size_t w0 = 0; w0 < n; w0 += (size_t)sigma) {          // longest rows first inside each window (stable: ties keep row order)
-            const size_t w1 = std::min(n, w0 + (size_t)sigma);
-            std::stable_sort(perm.begin() + w0, perm.begin() + w1, [&](int a, int b) {
-                return rowptr[a + 1] - rowptr[a] > rowptr[b + 1] - rowptr[b]; });
-        }
-        std::vector<int> sptr(ns + 1, 0);
+        std::vector<int> perm, sptr;
         size_t slots = 0;
-        for (size_t sl = 0; sl < ns; ++sl) {
-            int wmax = 0;
-            for (int l = 0; l < 32; ++l) { const int r = perm[sl * 32 + l]; if (r >= 0) wmax = std::max(wmax, rowptr[r + 1] - rowptr[r]); }
-            slots += (size_t)wmax * 32;
-            if (slots >= (size_t)INT32_MAX - 64) { set_error(__FILE__, __LINE__, "strip too large for sliced ELL"); return VEXB_ERR_UNSUPPORTED; }
-            sptr[sl + 1] = (int)slots;
+        if (!sell_layout(n, rowptr.data(), param("spmv.sell_sigma", 1024), perm, sptr, &slots)) {
+            set_error(__FILE__, __LINE__, "strip too large for sliced ELL");
+            return VEXB_ERR_UNSUPPORTED;
         }
+        const size_t ns = sptr.size() - 1;
         std::vector<int> scol(slots, -1);
         std::vector<T> sval(slots, T(0));
         for (size_t sl = 0; sl < ns; ++sl)
@@ -1407,6 +1395,27 @@ int vexb::spmat_from_csr(int dev, size_t nrows, size_t ncols, std::vector<int> &
 }
 
 using namespace vexb;
+
+// Host-only: the sliced-ELL layout VEXB_FMT_SELL would use for these row pointers (tests/test_hostlogic.py).
+extern "C" int vexb_csr_sell_layout(size_t nrows, const void *ptr, int ptr_bytes, long sigma, size_t *n_slices, size_t *n_slots,
+                                    int32_t *perm, int32_t *slice_ptr) {
+    VEXB_CHECK(ptr_bytes == 4 || ptr_bytes == 8, "ptr_bytes must be 4 or 8");
+    VEXB_CHECK((nrows == 0 || ptr) && n_slices && n_slots, "NULL argument");
+    std::vector<int> rp(nrows + 1, 0);
+    const int64_t p0 = nrows ? read_index(ptr, ptr_bytes, 0) : 0;
+    for (size_t i = 0; i <= nrows && nrows; ++i) {
+        const int64_t v = read_index(ptr, ptr_bytes, i) - p0;
+        VEXB_CHECK(v >= 0 && v < (int64_t)INT32_MAX && (i == 0 || v >= rp[i - 1]), "row pointers decrease or overflow at row %zu", i);
+        rp[i] = (int)v;
+    }
+    std::vector<int> pm, sp;
+    size_t slots = 0;
+    if (!sell_layout(nrows, rp.data(), sigma, pm, sp, &slots)) VEXB_FAIL(VEXB_ERR_UNSUPPORTED, "strip too large for sliced ELL");
+    *n_slices = sp.size() - 1; *n_slots = slots;
+    if (perm) std::copy(pm.begin(), pm.end(), perm);
+    if (slice_ptr) std::copy(sp.begin(), sp.end(), slice_ptr);
+    return VEXB_OK;
+}
 
 extern "C" int vexb_csr_create(int dev, void *stream, size_t nrows, size_t ncols,
                                const void *ptr, int ptr_bytes, const void *col, int col_bytes,
